@@ -1,0 +1,133 @@
+"""ctypes binding of libb200mf.so (the C ABI declared in include/b200mf.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C dealii_b200/csrc``.
+There is no fallback: if the shared library is missing, importing the engine fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mf.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOCONVERGENCE, ERR_COMM = 0, -1, -2, -3, -4, -5
+F64, F32 = 0, 1
+GEOMETRY_Q1_VERTICES, GEOMETRY_JACOBIANS = 0, 1
+CELLS_CARTESIAN, CELLS_AFFINE, CELLS_GENERAL = 0, 1, 2
+L2G_CONSTRAINED = 0x80000000
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_CHEBYSHEV = 0, 1, 2
+MESH_MORTON, MESH_LEXICOGRAPHIC = 0, 1
+DEFORM_NONE, DEFORM_SINE = 0, 1
+
+u64, u32p, u16p, f64p, vp = C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint16), C.POINTER(C.c_double), C.c_void_p
+
+
+class SetupDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("n_q_points_1d", C.c_int), ("number", C.c_int),
+                ("n_cells", u64), ("n_owned_dofs", u64), ("n_ghost_dofs", u64),
+                ("local_to_global", vp), ("constraint_mask", vp),
+                ("geometry", C.c_int), ("cell_vertices", vp), ("inv_jacobian", vp), ("JxW", vp),
+                ("shape_values", vp), ("shape_gradients_collocation", vp), ("quadrature_weights", vp),
+                ("subface_interpolation_matrix", vp),
+                ("constrained_dofs", vp), ("n_constrained_dofs", u64),
+                ("n_cells_interior", u64)]
+
+
+class SetupInfo(C.Structure):
+    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("n_q_points_1d", C.c_int), ("number", C.c_int),
+                ("n_cells", u64), ("n_owned_dofs", u64), ("n_ghost_dofs", u64), ("n_constrained_dofs", u64),
+                ("cell_kind", C.c_int), ("n_distinct_geometries", u64), ("device_bytes", u64),
+                ("geometry_bytes", u64), ("index_bytes", u64)]
+
+
+class Operator(C.Structure):
+    _fields_ = [("grad_coefficient", vp), ("mass_coefficient", vp),
+                ("grad_constant", C.c_double), ("mass_constant", C.c_double)]
+
+
+class SolverDesc(C.Structure):
+    _fields_ = [("preconditioner", C.c_int), ("inverse_diagonal", vp),
+                ("chebyshev_degree", C.c_int), ("smoothing_range", C.c_double),
+                ("eig_cg_n_iterations", C.c_int), ("safety_factor", C.c_double),
+                ("tolerance", C.c_double), ("max_iterations", C.c_int),
+                ("first_owned_global_index", u64)]
+
+
+class SolverResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("residual", C.c_double), ("initial_residual", C.c_double),
+                ("chebyshev_max_eigenvalue", C.c_double), ("chebyshev_min_eigenvalue", C.c_double),
+                ("operator_applications", u64)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("cells_per_direction", C.c_int),
+                ("cell_order", C.c_int), ("left", C.c_double), ("right", C.c_double),
+                ("deformation", C.c_int), ("deformation_amplitude", C.c_double),
+                ("dirichlet_boundary", C.c_int), ("mark_constrained_l2g", C.c_int)]
+
+
+class MeshView(C.Structure):
+    _fields_ = [("n_cells", u64), ("n_dofs", u64), ("n_boundary_dofs", u64),
+                ("dofs_per_cell", C.c_int), ("vertices_per_cell", C.c_int), ("dim", C.c_int),
+                ("local_to_global", u32p), ("cell_vertices", f64p), ("boundary_dofs", u32p)]
+
+
+# every symbol include/b200mf.h declares: (restype, argtypes)
+SYMBOLS = {
+    "b200mf_setup_create": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(vp)]),
+    "b200mf_setup_destroy": (C.c_int, [vp]),
+    "b200mf_setup_get_info": (C.c_int, [vp, C.POINTER(SetupInfo)]),
+    "b200mf_get_quadrature_points": (C.c_int, [vp, vp]),
+    "b200mf_cell_loop": (C.c_int, [vp, C.POINTER(Operator), vp, vp, vp]),
+    "b200mf_vmult": (C.c_int, [vp, C.POINTER(Operator), vp, vp, vp]),
+    "b200mf_copy_constrained_values": (C.c_int, [vp, vp, vp, vp]),
+    "b200mf_set_constrained_values": (C.c_int, [vp, vp, C.c_double, vp]),
+    "b200mf_compute_diagonal": (C.c_int, [vp, C.POINTER(Operator), vp, vp]),
+    "b200mf_vmult_host": (C.c_int, [vp, C.POINTER(Operator), vp, vp]),
+    "b200mf_vec_set": (C.c_int, [C.c_int, vp, C.c_double, u64, vp]),
+    "b200mf_vec_axpy": (C.c_int, [C.c_int, vp, C.c_double, vp, u64, vp]),
+    "b200mf_vec_sadd": (C.c_int, [C.c_int, vp, C.c_double, C.c_double, vp, u64, vp]),
+    "b200mf_vec_scale_by": (C.c_int, [C.c_int, vp, vp, vp, u64, vp]),
+    "b200mf_vec_dot": (C.c_int, [C.c_int, vp, vp, u64, f64p, vp]),
+    "b200mf_cg_solve": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
+                                  C.POINTER(SolverResult), vp]),
+    "b200mf_cg_solve_host": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
+                                       C.POINTER(SolverResult)]),
+    "b200mf_mesh_create": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(vp)]),
+    "b200mf_mesh_view_get": (C.c_int, [vp, C.POINTER(MeshView)]),
+    "b200mf_mesh_destroy": (C.c_int, [vp]),
+    "b200mf_setup_create_from_mesh": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "b200mf_last_error": (C.c_char_p, []),
+    "b200mf_version": (C.c_int, []),
+    "b200mf_kernel_launch_count": (u64, []),
+}
+
+_lib = None
+
+
+class B200MFError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"b200mf error {code}: {message}")
+        self.code = code
+
+
+def load():
+    """Load libb200mf.so (once) and declare the prototypes of every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError => a declared symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != OK:
+        raise B200MFError(code, load().b200mf_last_error().decode())
+    return code

@@ -1,0 +1,623 @@
+// C ABI entry points: setup (Portable::MatrixFree::reinit), operator application
+// (cell_loop / vmult / copy_constrained_values / compute_diagonal).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+#include "internal.h"
+#include "vector_ops.cuh"
+
+namespace b200mf {
+
+static thread_local std::string g_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+size_t number_size(int number) { return number == B200MF_F64 ? 8 : 4; }
+
+#define DECL_N(N)                                                                             \
+  int launch_cells_n##N(const Setup &, const b200mf_operator &, void *, const void *, uint64_t, \
+                        uint64_t, cudaStream_t, bool, double *);
+DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
+#undef DECL_N
+
+static int launch_cells(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                        uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot) {
+  switch (s.n) {
+    case 2: return launch_cells_n2(s, op, dst, src, b, e, st, diag, dot);
+    case 3: return launch_cells_n3(s, op, dst, src, b, e, st, diag, dot);
+    case 4: return launch_cells_n4(s, op, dst, src, b, e, st, diag, dot);
+    case 5: return launch_cells_n5(s, op, dst, src, b, e, st, diag, dot);
+    case 6: return launch_cells_n6(s, op, dst, src, b, e, st, diag, dot);
+    case 7: return launch_cells_n7(s, op, dst, src, b, e, st, diag, dot);
+    case 8: return launch_cells_n8(s, op, dst, src, b, e, st, diag, dot);
+    case 9: return launch_cells_n9(s, op, dst, src, b, e, st, diag, dot);
+  }
+  set_error("unsupported degree %d", s.degree);
+  return B200MF_ERR_UNSUPPORTED;
+}
+
+int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                     uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,
+                     double *dot_accum) {
+  return launch_cells(s, op, dst, src, cell_begin, cell_end, stream, false, dot_accum);
+}
+
+int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *diag,
+                            cudaStream_t stream) {
+  return launch_cells(s, op, diag, diag, 0, s.n_cells, stream, true, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// device-side geometry setup (replaces the host FEValues loop of
+// portable_matrix_free.templates.h:267-346)
+// ---------------------------------------------------------------------------------------
+template <int dim>
+__device__ inline void q1_jacobian(const double *v /*[2^dim][dim]*/, const double *xi,
+                                   double J[dim][dim], double *x /*[dim] or null*/) {
+  for (int d = 0; d < dim; ++d) {
+    for (int e = 0; e < dim; ++e) J[d][e] = 0.0;
+    if (x) x[d] = 0.0;
+  }
+  for (int k = 0; k < (1 << dim); ++k) {
+    double N = 1.0, dN[dim];
+    for (int e = 0; e < dim; ++e) dN[e] = 1.0;
+    for (int d = 0; d < dim; ++d) {
+      const int b = (k >> d) & 1;
+      const double f = b ? xi[d] : 1.0 - xi[d];
+      const double df = b ? 1.0 : -1.0;
+      N *= f;
+      for (int e = 0; e < dim; ++e) dN[e] *= (e == d) ? df : f;
+    }
+    for (int d = 0; d < dim; ++d) {
+      if (x) x[d] += N * v[k * dim + d];
+      for (int e = 0; e < dim; ++e) J[d][e] += dN[e] * v[k * dim + d];
+    }
+  }
+}
+
+template <int dim>
+__device__ inline double invert(const double J[dim][dim], double Ji[dim][dim]) {
+  if (dim == 2) {
+    const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double r = 1.0 / det;
+    Ji[0][0] = J[1][1] * r; Ji[0][1] = -J[0][1] * r;
+    Ji[1][0] = -J[1][0] * r; Ji[1][1] = J[0][0] * r;
+    return det;
+  } else {
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double r = 1.0 / det;
+    Ji[0][0] = c00 * r;
+    Ji[1][0] = c01 * r;
+    Ji[2][0] = c02 * r;
+    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+    return det;
+  }
+}
+
+// metric[cell][s][q] = w_q det(J) (J^-1 J^-T)_s (s over the upper triangle), jxw[cell][q]
+template <int dim, typename Number>
+__global__ void general_geometry_from_vertices(const double *vertices, const double *qp1d,
+                                               const double *qw1d, int n, uint64_t n_cells,
+                                               Number *metric, Number *jxw) {
+  const int nq = dim == 2 ? n * n : n * n * n;
+  constexpr int NS = dim * (dim + 1) / 2;
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_cells * nq) return;
+  const uint64_t cell = gid / nq;
+  const int q = (int)(gid - cell * nq);
+  int qi[3] = {q % n, (q / n) % n, q / (n * n)};
+  double xi[dim], w = 1.0;
+  for (int d = 0; d < dim; ++d) { xi[d] = qp1d[qi[d]]; w *= qw1d[qi[d]]; }
+  double J[dim][dim], Ji[dim][dim];
+  q1_jacobian<dim>(vertices + cell * (1 << dim) * dim, xi, J, nullptr);
+  const double det = invert<dim>(J, Ji);
+  // Ji[e][d] = d xi_e / d x_d
+  int s = 0;
+  for (int e = 0; e < dim; ++e)
+    for (int f = e; f < dim; ++f, ++s) {
+      double m = 0.0;
+      for (int d = 0; d < dim; ++d) m += Ji[e][d] * Ji[f][d];
+      metric[cell * (NS * nq) + s * nq + q] = Number(m * det * w);
+    }
+  jxw[cell * nq + q] = Number(det * w);
+}
+
+// same from the arrays Portable::MatrixFree stores (inv_jacobian(q,cell,d,e), JxW(q,cell))
+template <int dim, typename Number>
+__global__ void general_geometry_from_jacobians(const double *inv_jac, const double *jxw_in,
+                                                int nq, uint64_t n_cells, Number *metric,
+                                                Number *jxw) {
+  constexpr int NS = dim * (dim + 1) / 2;
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_cells * nq) return;
+  const uint64_t cell = gid / nq;
+  const int q = (int)(gid - cell * nq);
+  const double *Ji = inv_jac + gid * dim * dim; // [e][d]
+  const double jw = jxw_in[gid];
+  int s = 0;
+  for (int e = 0; e < dim; ++e)
+    for (int f = e; f < dim; ++f, ++s) {
+      double m = 0.0;
+      for (int d = 0; d < dim; ++d) m += Ji[e * dim + d] * Ji[f * dim + d];
+      metric[cell * (NS * nq) + s * nq + q] = Number(m * jw);
+    }
+  jxw[cell * nq + q] = Number(jw);
+}
+
+template <int dim>
+__global__ void quadrature_points_kernel(const double *vertices, const double *qp1d, int n,
+                                         uint64_t n_cells, double *out) {
+  const int nq = dim == 2 ? n * n : n * n * n;
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_cells * nq) return;
+  const uint64_t cell = gid / nq;
+  const int q = (int)(gid - cell * nq);
+  int qi[3] = {q % n, (q / n) % n, q / (n * n)};
+  double xi[dim], J[dim][dim], x[dim];
+  for (int d = 0; d < dim; ++d) xi[d] = qp1d[qi[d]];
+  q1_jacobian<dim>(vertices + cell * (1 << dim) * dim, xi, J, x);
+  for (int d = 0; d < dim; ++d) out[gid * dim + d] = x[d];
+}
+
+template <typename Number>
+__global__ void copy_constrained_kernel(Number *dst, const Number *src, const uint32_t *idx,
+                                        uint64_t n, double *dot_accum) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (i < n) {
+    const Number v = src[idx[i]];
+    dst[idx[i]] = v;
+    acc = double(v) * double(v);
+  }
+  if (dot_accum != nullptr) {
+    acc = block_sum(acc);
+    if (threadIdx.x == 0 && acc != 0.0) atomicAdd(dot_accum, acc);
+  }
+}
+template <typename Number>
+__global__ void set_constrained_kernel(Number *dst, Number value, const uint32_t *idx,
+                                       uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = value;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc_copy(T **dptr, const T *host, size_t count, Setup &s, uint64_t *bucket) {
+  B200MF_CUDA_CHECK(cudaMalloc((void **)dptr, std::max<size_t>(count, 1) * sizeof(T)));
+  if (count) B200MF_CUDA_CHECK(cudaMemcpy(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  s.device_bytes += count * sizeof(T);
+  if (bucket) *bucket += count * sizeof(T);
+  return B200MF_OK;
+}
+
+template <typename Number>
+static int upload_converted(void **dptr, const std::vector<double> &v, Setup &s, uint64_t *bucket) {
+  std::vector<Number> tmp(v.begin(), v.end());
+  Number *d = nullptr;
+  int rc = dev_alloc_copy<Number>(&d, tmp.data(), tmp.size(), s, bucket);
+  *dptr = d;
+  return rc;
+}
+
+// classify cells from their Q1 vertices and build the compressed affine table
+// (cf. MappingInfo cell types, matrix_free/mapping_info.templates.h:428-573)
+static int classify_and_compress(const b200mf_setup_desc &d, Setup &s,
+                                 std::vector<double> &table, std::vector<uint32_t> &geom_id) {
+  const int dim = d.dim, nv = 1 << dim;
+  int kind = B200MF_CELLS_CARTESIAN;
+  const double tol = 1e-12;
+  // pass 1: classification
+  for (uint64_t c = 0; c < d.n_cells && kind != B200MF_CELLS_GENERAL; ++c) {
+    const double *v = d.cell_vertices + c * nv * dim;
+    double E[3][3], scale = 0.0;
+    for (int e = 0; e < dim; ++e)
+      for (int k = 0; k < dim; ++k) {
+        E[k][e] = v[(1 << e) * dim + k] - v[k]; // J[k][e] = dx_k/dxi_e
+        scale = std::max(scale, std::fabs(E[k][e]));
+      }
+    bool affine = true;
+    for (int k = 0; k < nv && affine; ++k)
+      for (int x = 0; x < dim; ++x) {
+        double pred = v[x];
+        for (int e = 0; e < dim; ++e)
+          if ((k >> e) & 1) pred += E[x][e];
+        if (std::fabs(pred - v[k * dim + x]) > tol * scale) { affine = false; break; }
+      }
+    if (!affine) { kind = B200MF_CELLS_GENERAL; break; }
+    for (int e = 0; e < dim; ++e)
+      for (int k = 0; k < dim; ++k)
+        if (k != e && std::fabs(E[k][e]) > tol * scale) kind = B200MF_CELLS_AFFINE;
+  }
+  s.cell_kind = kind;
+  if (kind == B200MF_CELLS_GENERAL) return B200MF_OK;
+
+  // pass 2: table of distinct Jacobians
+  const int NS = dim * (dim + 1) / 2;
+  const int entry = (kind == B200MF_CELLS_CARTESIAN ? dim : NS) + 1;
+  std::map<std::vector<int64_t>, uint32_t> seen;
+  geom_id.resize(d.n_cells);
+  std::vector<int64_t> key(dim * dim);
+  double last[9];
+  uint32_t last_id = 0;
+  bool have_last = false;
+  for (uint64_t c = 0; c < d.n_cells; ++c) {
+    const double *v = d.cell_vertices + c * nv * dim;
+    double J[3][3], flat[9];
+    for (int e = 0; e < dim; ++e)
+      for (int k = 0; k < dim; ++k) {
+        J[k][e] = v[(1 << e) * dim + k] - v[k];
+        flat[k * dim + e] = J[k][e];
+      }
+    if (have_last) {
+      bool same = true;
+      for (int i = 0; i < dim * dim; ++i)
+        if (std::fabs(flat[i] - last[i]) > 1e-13 * std::fabs(last[0]) + 1e-300) { same = false; break; }
+      if (same) { geom_id[c] = last_id; continue; }
+    }
+    double scale = 0.0;
+    for (int i = 0; i < dim * dim; ++i) scale = std::max(scale, std::fabs(flat[i]));
+    // quantise relative to a power-of-two scale so that round-off equal cells collide
+    int ex;
+    std::frexp(scale, &ex);
+    for (int i = 0; i < dim * dim; ++i)
+      key[i] = (int64_t)std::llround(std::ldexp(flat[i], 40 - ex));
+    key.resize(dim * dim + 1);
+    key[dim * dim] = ex;
+    auto it = seen.find(key);
+    uint32_t id;
+    if (it == seen.end()) {
+      id = (uint32_t)seen.size();
+      seen.emplace(key, id);
+      // entry values
+      double Ji[3][3], det;
+      if (dim == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det;
+        Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+      } else {
+        const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+        Ji[0][0] = c00 / det; Ji[1][0] = c01 / det; Ji[2][0] = c02 / det;
+        Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+        Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+        Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+        Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+        Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+        Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+      }
+      if (kind == B200MF_CELLS_CARTESIAN) {
+        for (int e = 0; e < dim; ++e) table.push_back(Ji[e][e] * Ji[e][e] * det);
+      } else {
+        for (int e = 0; e < dim; ++e)
+          for (int f = e; f < dim; ++f) {
+            double m = 0.0;
+            for (int x = 0; x < dim; ++x) m += Ji[e][x] * Ji[f][x];
+            table.push_back(m * det);
+          }
+      }
+      table.push_back(det);
+    } else {
+      id = it->second;
+    }
+    key.resize(dim * dim);
+    geom_id[c] = id;
+    std::memcpy(last, flat, sizeof(double) * dim * dim);
+    last_id = id;
+    have_last = true;
+  }
+  s.n_geom = table.size() / entry;
+  return B200MF_OK;
+}
+
+} // namespace b200mf
+
+using namespace b200mf;
+
+namespace b200mf {
+int copy_constrained_impl(const Setup &s, void *dst, const void *src, cudaStream_t st,
+                                 double *dot_accum) {
+  if (s.n_constrained == 0) return B200MF_OK;
+  const unsigned blocks = (unsigned)((s.n_constrained + 255) / 256);
+  if (s.number == B200MF_F64)
+    copy_constrained_kernel<double><<<blocks, 256, 0, st>>>(
+        (double *)dst, (const double *)src, s.d_constrained, s.n_constrained, dot_accum);
+  else
+    copy_constrained_kernel<float><<<blocks, 256, 0, st>>>(
+        (float *)dst, (const float *)src, s.d_constrained, s.n_constrained, dot_accum);
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t st) {
+  if (s.n_constrained == 0) return B200MF_OK;
+  const unsigned blocks = (unsigned)((s.n_constrained + 255) / 256);
+  if (s.number == B200MF_F64)
+    set_constrained_kernel<double><<<blocks, 256, 0, st>>>((double *)dst, value, s.d_constrained,
+                                                           s.n_constrained);
+  else
+    set_constrained_kernel<float><<<blocks, 256, 0, st>>>((float *)dst, (float)value,
+                                                          s.d_constrained, s.n_constrained);
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+               cudaStream_t st, double *dot_accum) {
+  B200MF_CUDA_CHECK(cudaMemsetAsync(dst, 0, (s.n_owned + s.n_ghost) * number_size(s.number), st));
+  int rc = launch_cell_loop(s, op, dst, src, 0, s.n_cells, st, dot_accum);
+  if (rc != B200MF_OK) return rc;
+  return copy_constrained_impl(s, dst, src, st, dot_accum);
+}
+} // namespace b200mf
+
+
+extern "C" {
+
+const char *b200mf_last_error(void) { return g_error.c_str(); }
+int b200mf_version(void) { return B200MF_VERSION; }
+uint64_t b200mf_kernel_launch_count(void) { return g_launch_count.load(); }
+
+int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
+  B200MF_REQUIRE(d && out, "null argument");
+  B200MF_REQUIRE(d->dim == 2 || d->dim == 3, "dim must be 2 or 3 (got %d)", d->dim);
+  B200MF_REQUIRE(d->degree >= 1 && d->degree <= 8, "degree must be in 1..8 (got %d)", d->degree);
+  // same requirement as AssertThrow(n_q_points_1d >= fe_degree+1) in
+  // portable_matrix_free.templates.h:1243, tightened to equality in this release
+  B200MF_REQUIRE(d->n_q_points_1d == d->degree + 1,
+                 "n_q_points_1d must equal degree+1 (got %d for degree %d)", d->n_q_points_1d,
+                 d->degree);
+  B200MF_REQUIRE(d->number == B200MF_F64 || d->number == B200MF_F32, "bad number type");
+  B200MF_REQUIRE(d->local_to_global || d->n_cells == 0, "local_to_global is null");
+  B200MF_REQUIRE(d->n_owned_dofs + d->n_ghost_dofs < 0x80000000ull,
+                 "more than 2^31-1 local dofs per process are not supported");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+    set_error("no CUDA device available: the engine has no CPU fallback");
+    return B200MF_ERR_CUDA;
+  }
+  b200mf_setup *h = new b200mf_setup();
+  Setup &s = h->impl;
+  s.dim = d->dim; s.degree = d->degree; s.n = d->degree + 1; s.number = d->number;
+  s.n_cells = d->n_cells; s.n_owned = d->n_owned_dofs; s.n_ghost = d->n_ghost_dofs;
+  s.n_constrained = d->n_constrained_dofs; s.n_cells_interior = d->n_cells_interior;
+  s.dofs_per_cell = 1;
+  for (int i = 0; i < s.dim; ++i) s.dofs_per_cell *= s.n;
+  const int n = s.n, nq = s.dofs_per_cell;
+  int rc = B200MF_OK;
+#define TRY(x) do { rc = (x); if (rc != B200MF_OK) { b200mf_setup_destroy(h); return rc; } } while (0)
+
+  // --- shape data
+  build_fe_q_shape_data(s.degree, s.shape_values, s.shape_grad_colloc, s.q_weights,
+                        s.q_points_1d, s.subface);
+  if (d->shape_values) s.shape_values.assign(d->shape_values, d->shape_values + n * n);
+  if (d->shape_gradients_collocation)
+    s.shape_grad_colloc.assign(d->shape_gradients_collocation,
+                               d->shape_gradients_collocation + n * n);
+  if (d->quadrature_weights) s.q_weights.assign(d->quadrature_weights, d->quadrature_weights + n);
+  if (d->subface_interpolation_matrix)
+    s.subface.assign(d->subface_interpolation_matrix, d->subface_interpolation_matrix + n * n);
+
+  // --- indices
+  TRY(dev_alloc_copy<uint32_t>(&s.d_l2g, d->local_to_global, d->n_cells * nq, s, &s.index_bytes));
+  if (d->constraint_mask) {
+    for (uint64_t c = 0; c < d->n_cells; ++c)
+      if (d->constraint_mask[c]) { s.any_mask = true; break; }
+    if (s.any_mask)
+      TRY(dev_alloc_copy<uint16_t>(&s.d_mask, d->constraint_mask, d->n_cells, s, &s.index_bytes));
+  }
+  if (d->n_constrained_dofs)
+    TRY(dev_alloc_copy<uint32_t>(&s.d_constrained, d->constrained_dofs, d->n_constrained_dofs, s,
+                                 &s.index_bytes));
+  if (s.number == B200MF_F64) TRY(upload_converted<double>(&s.d_weights, s.subface, s, nullptr));
+  else                        TRY(upload_converted<float>(&s.d_weights, s.subface, s, nullptr));
+
+  // --- geometry
+  double *d_qp = nullptr, *d_qw = nullptr;
+  TRY(dev_alloc_copy<double>(&d_qp, s.q_points_1d.data(), n, s, nullptr));
+  TRY(dev_alloc_copy<double>(&d_qw, s.q_weights.data(), n, s, nullptr));
+  const size_t NS = s.dim * (s.dim + 1) / 2;
+  const size_t ns = number_size(s.number);
+  const uint64_t total_q = d->n_cells * (uint64_t)nq;
+  const unsigned blocks = (unsigned)((total_q + 255) / 256);
+  if (d->geometry == B200MF_GEOMETRY_Q1_VERTICES) {
+    B200MF_REQUIRE(d->cell_vertices || d->n_cells == 0, "cell_vertices is null");
+    std::vector<double> table;
+    std::vector<uint32_t> geom_id;
+    TRY(classify_and_compress(*d, s, table, geom_id));
+    const size_t nvd = (size_t)(1 << s.dim) * s.dim;
+    if (s.cell_kind == B200MF_CELLS_GENERAL) {
+      double *d_vert = nullptr;
+      B200MF_CUDA_CHECK(cudaMalloc((void **)&d_vert, std::max<size_t>(d->n_cells * nvd, 1) * 8));
+      B200MF_CUDA_CHECK(cudaMemcpy(d_vert, d->cell_vertices, d->n_cells * nvd * 8,
+                                   cudaMemcpyHostToDevice));
+      B200MF_CUDA_CHECK(cudaMalloc(&s.d_metric, std::max<size_t>(total_q * NS * ns, 1)));
+      B200MF_CUDA_CHECK(cudaMalloc(&s.d_jxw, std::max<size_t>(total_q * ns, 1)));
+      s.geometry_bytes += total_q * (NS + 1) * ns;
+      if (total_q) {
+        if (s.dim == 2 && s.number == B200MF_F64)
+          general_geometry_from_vertices<2, double><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+        else if (s.dim == 2)
+          general_geometry_from_vertices<2, float><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+        else if (s.number == B200MF_F64)
+          general_geometry_from_vertices<3, double><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+        else
+          general_geometry_from_vertices<3, float><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+        count_launch();
+      }
+      B200MF_CUDA_CHECK(cudaDeviceSynchronize());
+      cudaFree(d_vert);
+    } else {
+      if (s.number == B200MF_F64) TRY(upload_converted<double>(&s.d_geom_table, table, s, &s.geometry_bytes));
+      else                        TRY(upload_converted<float>(&s.d_geom_table, table, s, &s.geometry_bytes));
+      if (s.n_geom > 1)
+        TRY(dev_alloc_copy<uint32_t>(&s.d_geom_id, geom_id.data(), geom_id.size(), s, &s.geometry_bytes));
+    }
+    // keep the vertices for quadrature point queries while they are small
+    if (d->n_cells * nvd * 8 <= (512ull << 20)) {
+      s.h_vertices.assign(d->cell_vertices, d->cell_vertices + d->n_cells * nvd);
+      s.has_vertices = true;
+    }
+  } else if (d->geometry == B200MF_GEOMETRY_JACOBIANS) {
+    B200MF_REQUIRE(d->inv_jacobian && d->JxW, "inv_jacobian / JxW is null");
+    s.cell_kind = B200MF_CELLS_GENERAL;
+    double *d_ij = nullptr, *d_jw = nullptr;
+    const size_t dd = (size_t)s.dim * s.dim;
+    B200MF_CUDA_CHECK(cudaMalloc((void **)&d_ij, std::max<size_t>(total_q * dd, 1) * 8));
+    B200MF_CUDA_CHECK(cudaMalloc((void **)&d_jw, std::max<size_t>(total_q, 1) * 8));
+    B200MF_CUDA_CHECK(cudaMemcpy(d_ij, d->inv_jacobian, total_q * dd * 8, cudaMemcpyHostToDevice));
+    B200MF_CUDA_CHECK(cudaMemcpy(d_jw, d->JxW, total_q * 8, cudaMemcpyHostToDevice));
+    B200MF_CUDA_CHECK(cudaMalloc(&s.d_metric, std::max<size_t>(total_q * NS * ns, 1)));
+    B200MF_CUDA_CHECK(cudaMalloc(&s.d_jxw, std::max<size_t>(total_q * ns, 1)));
+    s.geometry_bytes += total_q * (NS + 1) * ns;
+    if (total_q) {
+      if (s.dim == 2 && s.number == B200MF_F64)
+        general_geometry_from_jacobians<2, double><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+      else if (s.dim == 2)
+        general_geometry_from_jacobians<2, float><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+      else if (s.number == B200MF_F64)
+        general_geometry_from_jacobians<3, double><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+      else
+        general_geometry_from_jacobians<3, float><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+      count_launch();
+    }
+    B200MF_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(d_ij);
+    cudaFree(d_jw);
+  } else {
+    delete h;
+    set_error("unknown geometry input kind %d", d->geometry);
+    return B200MF_ERR_INVALID;
+  }
+  cudaFree(d_qp);
+  cudaFree(d_qw);
+  s.device_bytes += s.geometry_bytes;
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_scratch, 4096 * sizeof(double)));
+  B200MF_CUDA_CHECK(cudaMallocHost((void **)&s.h_pinned, 64 * sizeof(double)));
+  B200MF_CUDA_CHECK(cudaGetLastError());
+#undef TRY
+  *out = h;
+  return B200MF_OK;
+}
+
+int b200mf_setup_destroy(b200mf_setup *h) {
+  if (!h) return B200MF_OK;
+  Setup *s = &h->impl;
+  cudaFree(s->d_l2g); cudaFree(s->d_mask); cudaFree(s->d_geom_id); cudaFree(s->d_geom_table);
+  cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
+  cudaFree(s->d_qpoints); cudaFree(s->d_scratch);
+  if (s->h_pinned) cudaFreeHost(s->h_pinned);
+  for (void *w : s->d_work) cudaFree(w);
+  for (void *w : s->d_stage) cudaFree(w);
+  delete h;
+  return B200MF_OK;
+}
+
+int b200mf_setup_get_info(const b200mf_setup *h, b200mf_setup_info *info) {
+  B200MF_REQUIRE(h && info, "null argument");
+  const Setup &s = h->impl;
+  info->dim = s.dim; info->degree = s.degree; info->n_q_points_1d = s.n; info->number = s.number;
+  info->n_cells = s.n_cells; info->n_owned_dofs = s.n_owned; info->n_ghost_dofs = s.n_ghost;
+  info->n_constrained_dofs = s.n_constrained; info->cell_kind = s.cell_kind;
+  info->n_distinct_geometries = s.n_geom; info->device_bytes = s.device_bytes;
+  info->geometry_bytes = s.geometry_bytes; info->index_bytes = s.index_bytes;
+  return B200MF_OK;
+}
+
+int b200mf_get_quadrature_points(const b200mf_setup *h, double *out_host) {
+  B200MF_REQUIRE(h && out_host, "null argument");
+  const Setup &s = h->impl;
+  B200MF_REQUIRE(s.has_vertices, "quadrature points need a setup created from Q1 vertices");
+  const size_t nvd = (size_t)(1 << s.dim) * s.dim;
+  const uint64_t total_q = s.n_cells * (uint64_t)s.dofs_per_cell;
+  double *d_vert = nullptr, *d_qp = nullptr, *d_out = nullptr;
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&d_vert, std::max<size_t>(s.n_cells * nvd, 1) * 8));
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&d_qp, s.n * 8));
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&d_out, std::max<size_t>(total_q * s.dim, 1) * 8));
+  B200MF_CUDA_CHECK(cudaMemcpy(d_vert, s.h_vertices.data(), s.n_cells * nvd * 8, cudaMemcpyHostToDevice));
+  B200MF_CUDA_CHECK(cudaMemcpy(d_qp, s.q_points_1d.data(), s.n * 8, cudaMemcpyHostToDevice));
+  const unsigned blocks = (unsigned)((total_q + 255) / 256);
+  if (total_q) {
+    if (s.dim == 2) quadrature_points_kernel<2><<<blocks, 256>>>(d_vert, d_qp, s.n, s.n_cells, d_out);
+    else            quadrature_points_kernel<3><<<blocks, 256>>>(d_vert, d_qp, s.n, s.n_cells, d_out);
+    count_launch();
+  }
+  B200MF_CUDA_CHECK(cudaMemcpy(out_host, d_out, total_q * s.dim * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_vert); cudaFree(d_qp); cudaFree(d_out);
+  return B200MF_OK;
+}
+
+int b200mf_cell_loop(const b200mf_setup *h, const b200mf_operator *op, void *dst, const void *src,
+                     void *stream) {
+  B200MF_REQUIRE(h && op && dst && src, "null argument");
+  return launch_cell_loop(h->impl, *op, dst, src, 0, h->impl.n_cells, (cudaStream_t)stream, nullptr);
+}
+
+int b200mf_copy_constrained_values(const b200mf_setup *h, void *dst, const void *src,
+                                   void *stream) {
+  B200MF_REQUIRE(h && dst && src, "null argument");
+  return copy_constrained_impl(h->impl, dst, src, (cudaStream_t)stream, nullptr);
+}
+
+int b200mf_set_constrained_values(const b200mf_setup *h, void *dst, double value, void *stream) {
+  B200MF_REQUIRE(h && dst, "null argument");
+  return set_constrained_impl(h->impl, dst, value, (cudaStream_t)stream);
+}
+
+int b200mf_vmult(const b200mf_setup *h, const b200mf_operator *op, void *dst, const void *src,
+                 void *stream) {
+  B200MF_REQUIRE(h && op && dst && src, "null argument");
+  return vmult_impl(h->impl, *op, dst, src, (cudaStream_t)stream, nullptr);
+}
+
+int b200mf_compute_diagonal(const b200mf_setup *h, const b200mf_operator *op, void *diag,
+                            void *stream) {
+  B200MF_REQUIRE(h && op && diag, "null argument");
+  const Setup &s = h->impl;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200MF_CUDA_CHECK(cudaMemsetAsync(diag, 0, (s.n_owned + s.n_ghost) * number_size(s.number), st));
+  int rc = launch_compute_diagonal(s, *op, diag, st);
+  if (rc != B200MF_OK) return rc;
+  return b200mf_set_constrained_values(h, diag, 1.0, stream);
+}
+
+int b200mf_vmult_host(const b200mf_setup *h, const b200mf_operator *op, void *dst_host,
+                      const void *src_host) {
+  B200MF_REQUIRE(h && op && dst_host && src_host, "null argument");
+  Setup &s = const_cast<Setup &>(h->impl);
+  const size_t bytes = (s.n_owned + s.n_ghost) * number_size(s.number);
+  for (int i = 0; i < 2; ++i)
+    if (!s.d_stage[i]) B200MF_CUDA_CHECK(cudaMalloc(&s.d_stage[i], std::max<size_t>(bytes, 1)));
+  B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_stage[0], src_host, bytes, cudaMemcpyHostToDevice, 0));
+  int rc = b200mf_vmult(h, op, s.d_stage[1], s.d_stage[0], nullptr);
+  if (rc != B200MF_OK) return rc;
+  B200MF_CUDA_CHECK(cudaMemcpyAsync(dst_host, s.d_stage[1], s.n_owned * number_size(s.number),
+                                    cudaMemcpyDeviceToHost, 0));
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(0));
+  return B200MF_OK;
+}
+
+} // extern "C"

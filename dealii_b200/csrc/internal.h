@@ -1,0 +1,135 @@
+// Internal declarations shared by the translation units of libb200mf.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mf.h"
+
+namespace b200mf {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define B200MF_CUDA_CHECK(expr)                                                          \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      ::b200mf::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,             \
+                          cudaGetErrorString(err__));                                    \
+      return B200MF_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define B200MF_REQUIRE(cond, ...)                                                        \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ::b200mf::set_error(__VA_ARGS__);                                                  \
+      return B200MF_ERR_INVALID;                                                         \
+    }                                                                                    \
+  } while (0)
+
+constexpr int kMaxN = 9; // degree <= 8
+
+// Even-odd packed 1D matrix for out[q] = sum_i M[i][q] in[i] with
+// M[n-1-i][n-1-q] = +/- M[i][q]  (cf. shape_info.templates.h:1153-1180 convert_to_eo).
+//   E[i*hq + q] = (M[i][q] + M[i][n-1-q]) / 2,  i < h, q < hq
+//   O[i*h  + q] = (M[i][q] - M[i][n-1-q]) / 2,  i < h, q < h
+//   mid[q]      = M[(n-1)/2][q],                q < hq   (n odd only)
+// with h = n/2, hq = (n+1)/2.
+template <typename Number, int n>
+struct EoMatrix {
+  static constexpr int h = n / 2, hq = (n + 1) / 2;
+  Number E[h * hq > 0 ? h * hq : 1];
+  Number O[h * h > 0 ? h * h : 1];
+  Number mid[hq];
+};
+
+template <typename Number, int n>
+struct ShapeData {
+  EoMatrix<Number, n> S;  // dofs -> quadrature points (symmetric)
+  EoMatrix<Number, n> St; // quadrature points -> dofs
+  EoMatrix<Number, n> D;  // collocation derivative (skew-symmetric)
+  EoMatrix<Number, n> Dt;
+  Number w[n];            // 1D quadrature weights
+};
+
+// Host-side description of the operator passed to the kernels.
+template <typename Number>
+struct OperatorArgs {
+  const Number *grad_coef;
+  const Number *mass_coef;
+  Number grad_const;
+  Number mass_const;
+  int has_mass;
+};
+
+struct Setup {
+  int dim = 0, degree = 0, n = 0, number = 0;
+  uint64_t n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0, n_cells_interior = 0;
+  int dofs_per_cell = 0;
+  int cell_kind = B200MF_CELLS_GENERAL;
+  uint64_t n_geom = 0;
+
+  // device arrays
+  uint32_t *d_l2g = nullptr;
+  uint16_t *d_mask = nullptr;
+  uint32_t *d_geom_id = nullptr;   // per cell index into d_geom_table (null if table has 1 entry)
+  void *d_geom_table = nullptr;    // cartesian: [n_geom][4]; affine: [n_geom][7]  (Number)
+  void *d_metric = nullptr;        // general: [n_cells][6 or 3][n_q_total] merged w*det*J^-1 J^-T
+  void *d_jxw = nullptr;           // general: [n_cells][n_q_total]
+  uint32_t *d_constrained = nullptr;
+  void *d_weights = nullptr;       // subface interpolation matrix [n*n] (Number)
+  double *d_qpoints = nullptr;     // optional cache
+  // host copies needed later
+  std::vector<double> shape_values, shape_grad_colloc, q_weights, q_points_1d, subface;
+  std::vector<double> h_vertices;  // kept only when small (quadrature point queries)
+  bool has_vertices = false;
+  bool any_mask = false;
+  uint64_t device_bytes = 0, geometry_bytes = 0, index_bytes = 0;
+
+  // scratch for reductions / solver
+  double *d_scratch = nullptr;
+  double *h_pinned = nullptr;
+  void *d_work[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t work_elems = 0;
+  // staging buffers for the *_host entry points
+  void *d_stage[2] = {nullptr, nullptr};
+};
+
+size_t number_size(int number);
+
+// dst = 0; cell loop; copy_constrained_values -- optionally accumulating src.dst into
+// *dot_accum (device double) on the way
+int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+               cudaStream_t stream, double *dot_accum);
+int copy_constrained_impl(const Setup &s, void *dst, const void *src, cudaStream_t st,
+                          double *dot_accum);
+int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t st);
+
+// kernels_dispatch.cu
+int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                     uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,
+                     double *dot_accum);
+int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *diag,
+                            cudaStream_t stream);
+
+// shape.cpp
+void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
+                           std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
+                           std::vector<double> &q_points, std::vector<double> &subface);
+
+template <typename Number, int n>
+void fill_shape_data(const Setup &s, ShapeData<Number, n> &out);
+
+} // namespace b200mf
+
+struct b200mf_setup {
+  b200mf::Setup impl;
+};

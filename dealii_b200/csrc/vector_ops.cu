@@ -1,0 +1,105 @@
+// BLAS-1 entry points (LinearAlgebra::distributed::Vector<Number, MemorySpace::Default>,
+// lac/vector_operations_internal.h:2140-2660).  Grid-stride kernels, 148-SM sized grids.
+#include "vector_ops.cuh"
+
+namespace b200mf {
+
+template <typename Number>
+__global__ void set_kernel(Number *x, Number v, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+template <typename Number>
+__global__ void sadd_kernel(Number *y, Number s, Number a, const Number *x, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    y[i] = s * y[i] + a * x[i];
+}
+template <typename Number>
+__global__ void scale_by_kernel(Number *y, const Number *d, const Number *x, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    y[i] = d[i] * x[i];
+}
+template <typename Number>
+__global__ void dot_kernel(const Number *x, const Number *y, uint64_t n, double *out) {
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    acc += double(x[i]) * double(y[i]);
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+template <typename Number>
+int dot_impl(const void *x, const void *y, uint64_t n, double *result_host, cudaStream_t st) {
+  double *d_out = nullptr;
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&d_out, sizeof(double)));
+  B200MF_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double), st));
+  dot_kernel<Number><<<vec_grid(n), kVecThreads, 0, st>>>((const Number *)x, (const Number *)y, n, d_out);
+  count_launch();
+  B200MF_CUDA_CHECK(cudaMemcpyAsync(result_host, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(d_out);
+  return B200MF_OK;
+}
+
+} // namespace b200mf
+
+using namespace b200mf;
+
+#define DISPATCH(number, call64, call32)                 \
+  do {                                                   \
+    if ((number) == B200MF_F64) { call64; }              \
+    else if ((number) == B200MF_F32) { call32; }         \
+    else { set_error("bad number type"); return B200MF_ERR_INVALID; } \
+  } while (0)
+
+extern "C" {
+
+int b200mf_vec_set(int number, void *x, double value, uint64_t n, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(number, (set_kernel<double><<<vec_grid(n), kVecThreads, 0, st>>>((double *)x, value, n)),
+           (set_kernel<float><<<vec_grid(n), kVecThreads, 0, st>>>((float *)x, (float)value, n)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+int b200mf_vec_sadd(int number, void *y, double s, double a, const void *x, uint64_t n,
+                    void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(number,
+           (sadd_kernel<double><<<vec_grid(n), kVecThreads, 0, st>>>((double *)y, s, a, (const double *)x, n)),
+           (sadd_kernel<float><<<vec_grid(n), kVecThreads, 0, st>>>((float *)y, (float)s, (float)a, (const float *)x, n)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+int b200mf_vec_axpy(int number, void *y, double a, const void *x, uint64_t n, void *stream) {
+  return b200mf_vec_sadd(number, y, 1.0, a, x, n, stream);
+}
+
+int b200mf_vec_scale_by(int number, void *y, const void *d, const void *x, uint64_t n,
+                        void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(number,
+           (scale_by_kernel<double><<<vec_grid(n), kVecThreads, 0, st>>>((double *)y, (const double *)d, (const double *)x, n)),
+           (scale_by_kernel<float><<<vec_grid(n), kVecThreads, 0, st>>>((float *)y, (const float *)d, (const float *)x, n)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+int b200mf_vec_dot(int number, const void *x, const void *y, uint64_t n, double *result_host,
+                   void *stream) {
+  B200MF_REQUIRE(result_host, "null result pointer");
+  if (number == B200MF_F64) return dot_impl<double>(x, y, n, result_host, (cudaStream_t)stream);
+  if (number == B200MF_F32) return dot_impl<float>(x, y, n, result_host, (cudaStream_t)stream);
+  set_error("bad number type");
+  return B200MF_ERR_INVALID;
+}
+
+} // extern "C"

@@ -1,0 +1,265 @@
+/* b200mf.h -- C ABI of the B200-native matrix-free operator engine.
+ *
+ * This is the drop-in boundary for deal.II's matrix-free hot path.  Every entry point
+ * names the reference interface it replaces (paths relative to the deal.II tree,
+ * 9.9.0-pre).  Conventions:
+ *   - every function returns B200MF_OK (0) or a negative error code;
+ *     b200mf_last_error() returns a thread-local message (replaces Assert/AssertThrow,
+ *     include/deal.II/base/exceptions.h, which cannot cross a C ABI);
+ *   - "device pointer" = plain CUDA device address in the caller's current device;
+ *     vectors are caller-owned arrays of `number` laid out as
+ *     LinearAlgebra::distributed::Vector stores them: [locally owned | ghosts]
+ *     (include/deal.II/lac/la_parallel_vector.h, base/partitioner.h:199);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream), work is
+ *     enqueued asynchronously unless stated otherwise;
+ *   - local dof order inside a cell is lexicographic, x fastest
+ *     (matrix_free/portable_matrix_free.templates.h:296-298).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * B200MF_ERR_CUDA.
+ */
+#ifndef B200MF_H
+#define B200MF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MF_VERSION 100 /* 0.1.0 */
+
+enum {
+  B200MF_OK = 0,
+  B200MF_ERR_INVALID = -1, /* bad argument (AssertThrow in the reference)        */
+  B200MF_ERR_CUDA = -2,    /* CUDA runtime/driver failure, or no device           */
+  B200MF_ERR_UNSUPPORTED = -3,
+  B200MF_ERR_NOCONVERGENCE = -4, /* SolverControl::NoConvergence, lac/solver_control.h */
+  B200MF_ERR_COMM = -5
+};
+
+enum { B200MF_F64 = 0, B200MF_F32 = 1 };
+
+/* How the cell geometry is handed over.  The engine classifies every cell as
+ * cartesian / affine / general like internal::MatrixFreeFunctions::MappingInfo
+ * (matrix_free/mapping_info.templates.h:428-573) and stores one Jacobian per
+ * distinct affine cell and merged metric terms per quadrature point otherwise. */
+enum {
+  B200MF_GEOMETRY_Q1_VERTICES = 0, /* cell_vertices[n_cells][2^dim][dim], MappingQ1      */
+  B200MF_GEOMETRY_JACOBIANS = 1    /* the arrays Portable::MatrixFree stores:
+                                      inv_jacobian[n_cells][n_q][dim][dim] and
+                                      JxW[n_cells][n_q]
+                                      (portable_matrix_free.templates.h:325-338)         */
+};
+
+enum { B200MF_CELLS_CARTESIAN = 0, B200MF_CELLS_AFFINE = 1, B200MF_CELLS_GENERAL = 2 };
+
+/* Bit 31 of a local_to_global entry marks a dof that CPU MatrixFree would have dropped
+ * from the cell's index list (constrained: read as 0, never written;
+ * matrix_free/fe_evaluation.h:3059-3171).  Portable::MatrixFree semantics = bit never set. */
+#define B200MF_L2G_CONSTRAINED 0x80000000u
+
+typedef struct b200mf_setup b200mf_setup;
+typedef struct b200mf_mesh b200mf_mesh;
+typedef struct b200mf_comm b200mf_comm;
+
+/* ------------------------------------------------------------------------------------
+ * Setup.  Replaces Portable::MatrixFree<dim,Number>::reinit(mapping, dof_handler,
+ * constraints, Quadrature<1>, AdditionalData)  (matrix_free/portable_matrix_free.h:480-527,
+ * impl portable_matrix_free.templates.h:1021-1433).  All pointers are HOST pointers, the
+ * engine copies what it needs to the device and owns it.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int dim;           /* 2 or 3                                                          */
+  int degree;        /* FE_Q degree p, 1..8                                             */
+  int n_q_points_1d; /* QGauss points per direction; this release requires p+1         */
+  int number;        /* B200MF_F64 / B200MF_F32: arithmetic AND vector element type     */
+  uint64_t n_cells;  /* locally owned cells                                             */
+  uint64_t n_owned_dofs; /* Partitioner::locally_owned_size()                           */
+  uint64_t n_ghost_dofs; /* Partitioner::n_ghost_indices()                              */
+
+  /* [n_cells][(p+1)^dim] process-local indices, lexicographic, hanging-node entries
+   * already redirected to the coarse neighbour as HangingNodes::setup_constraints does
+   * (matrix_free/hanging_nodes_internal.h:852-880).                                    */
+  const uint32_t *local_to_global;
+  /* [n_cells] ConstraintKinds bit masks (hanging_nodes_internal.h:40-60) or NULL.       */
+  const uint16_t *constraint_mask;
+
+  int geometry; /* B200MF_GEOMETRY_*                                                     */
+  const double *cell_vertices; /* Q1_VERTICES                                           */
+  const double *inv_jacobian;  /* JACOBIANS                                             */
+  const double *JxW;           /* JACOBIANS                                             */
+
+  /* 1D shape data exactly as internal::MatrixFreeFunctions::ShapeInfo holds it
+   * (matrix_free/shape_info.templates.h:895-898, 973-984), row-major [i*n_q + q].
+   * NULL => the engine builds FE_Q(p) (Gauss-Lobatto nodes) x QGauss(p+1) itself.       */
+  const double *shape_values;
+  const double *shape_gradients_collocation;
+  const double *quadrature_weights;           /* [n_q]                                  */
+  const double *subface_interpolation_matrix; /* [n][n] constraint_weights, or NULL     */
+
+  /* local indices (< n_owned_dofs) of constrained dofs, the list
+   * copy_constrained_values() walks (portable_matrix_free.templates.h:1366-1425).       */
+  const uint32_t *constrained_dofs;
+  uint64_t n_constrained_dofs;
+
+  /* Cells [0, n_cells_interior) touch no ghost dof and may run while the ghost exchange
+   * is in flight (the colour-0/2 vs colour-1 split of
+   * portable_matrix_free.templates.h:1090-1133).  0 => no split.                        */
+  uint64_t n_cells_interior;
+} b200mf_setup_desc;
+
+int b200mf_setup_create(const b200mf_setup_desc *desc, b200mf_setup **out);
+int b200mf_setup_destroy(b200mf_setup *s);
+
+/* Introspection (PMF::memory_consumption, get_padding_length & friends). */
+typedef struct {
+  int dim, degree, n_q_points_1d, number;
+  uint64_t n_cells, n_owned_dofs, n_ghost_dofs, n_constrained_dofs;
+  int cell_kind;                  /* B200MF_CELLS_* of the stored geometry               */
+  uint64_t n_distinct_geometries; /* affine compression table size                       */
+  uint64_t device_bytes;          /* total device memory owned by the setup              */
+  uint64_t geometry_bytes, index_bytes;
+} b200mf_setup_info;
+int b200mf_setup_get_info(const b200mf_setup *s, b200mf_setup_info *info);
+
+/* Quadrature point coordinates, the input of PMF::evaluate_coefficients functors
+ * (portable_matrix_free.h:585, get_quadrature_point :417): writes
+ * out[(cell*n_q_total + q)*dim + d] to a HOST array. */
+int b200mf_get_quadrature_points(const b200mf_setup *s, double *out_host);
+
+/* ------------------------------------------------------------------------------------
+ * Operator.  The user functor of Portable::MatrixFree::cell_loop cannot cross a C ABI;
+ * the engine implements the functor family of the reference's tests, tutorials and
+ * MatrixFreeOperators:   (c_grad grad u, grad v) + (c_mass u, v)
+ *   Laplace  : tests/performance/timing_matrix_free_kokkos.cc:129-152,
+ *              MatrixFreeOperators::LaplaceOperator (matrix_free/operators.h:892)
+ *   Helmholtz: examples/step-64/step-64.cc:120-219
+ * Coefficients are device arrays [n_cells * n_q^dim] indexed like
+ * PMF::Data::local_q_point_id (portable_matrix_free.h:400-415) or NULL.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  const void *grad_coefficient; /* NULL => 1                                            */
+  const void *mass_coefficient; /* NULL => no mass term unless mass_constant != 0       */
+  double grad_constant;         /* multiplies the gradient term (1 for Laplace)         */
+  double mass_constant;         /* constant mass coefficient (0 => none)                */
+} b200mf_operator;
+
+/* Portable::MatrixFree::cell_loop(func, src, dst): dst += sum_cells P^T A_cell P src
+ * (portable_matrix_free.h:562; serial_cell_loop portable_matrix_free.templates.h:1440). */
+int b200mf_cell_loop(const b200mf_setup *s, const b200mf_operator *op, void *dst,
+                     const void *src, void *stream);
+/* Operator::vmult of the reference's users: dst = 0; cell_loop; copy_constrained_values
+ * (examples/step-64/step-64.cc:313-325; MatrixFreeOperators::Base::vmult
+ * matrix_free/operators.h:1487 for setups built with B200MF_L2G_CONSTRAINED bits).      */
+int b200mf_vmult(const b200mf_setup *s, const b200mf_operator *op, void *dst,
+                 const void *src, void *stream);
+/* PMF::copy_constrained_values / set_constrained_values
+ * (portable_matrix_free.templates.h:711-751, 780-820).                                  */
+int b200mf_copy_constrained_values(const b200mf_setup *s, void *dst, const void *src,
+                                   void *stream);
+int b200mf_set_constrained_values(const b200mf_setup *s, void *dst, double value,
+                                  void *stream);
+/* MatrixFreeTools::compute_diagonal for Portable::MatrixFree (matrix_free/tools.h:1392-1569):
+ * diag_i = A_ii, constrained entries = 1.                                               */
+int b200mf_compute_diagonal(const b200mf_setup *s, const b200mf_operator *op, void *diag,
+                            void *stream);
+/* Same call with HOST vectors (copies inside): the end-to-end path of bench.py.          */
+int b200mf_vmult_host(const b200mf_setup *s, const b200mf_operator *op, void *dst_host,
+                      const void *src_host);
+
+/* ------------------------------------------------------------------------------------
+ * Vector kernels: LinearAlgebra::distributed::Vector<Number, MemorySpace::Default>
+ * BLAS-1 (lac/vector_operations_internal.h:2140-2660).  n counts elements of `number`.
+ * Reductions return through a HOST pointer after synchronising `stream`.
+ * ---------------------------------------------------------------------------------- */
+int b200mf_vec_set(int number, void *x, double value, uint64_t n, void *stream);
+int b200mf_vec_axpy(int number, void *y, double a, const void *x, uint64_t n, void *stream);
+int b200mf_vec_sadd(int number, void *y, double s, double a, const void *x, uint64_t n,
+                    void *stream); /* y = s*y + a*x */
+int b200mf_vec_scale_by(int number, void *y, const void *d, const void *x, uint64_t n,
+                        void *stream); /* y = d .* x  (DiagonalMatrix::vmult)            */
+int b200mf_vec_dot(int number, const void *x, const void *y, uint64_t n, double *result_host,
+                   void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Solver.  SolverCG<LA::d::Vector>::solve (lac/solver_cg.h:1391) with
+ * PreconditionIdentity, DiagonalMatrix (Jacobi, lac/diagonal_matrix.h:435) or
+ * PreconditionChebyshev over Jacobi (lac/precondition.h:3928-4121), vector updates and
+ * dot products fused around the operator kernel.
+ * ---------------------------------------------------------------------------------- */
+enum { B200MF_PRECOND_NONE = 0, B200MF_PRECOND_JACOBI = 1, B200MF_PRECOND_CHEBYSHEV = 2 };
+
+typedef struct {
+  int preconditioner;
+  const void *inverse_diagonal; /* device, [n_owned]; JACOBI / CHEBYSHEV                  */
+  /* PreconditionChebyshev::AdditionalData (lac/precondition.h:2121-2175)                */
+  int chebyshev_degree;
+  double smoothing_range;
+  int eig_cg_n_iterations;
+  double safety_factor; /* 0 => 1.2                                                      */
+  double tolerance;     /* absolute, on ||r||_2 (SolverControl)                          */
+  int max_iterations;
+  uint64_t first_owned_global_index; /* for the Chebyshev initial guess (global i % 11)   */
+} b200mf_solver_desc;
+
+typedef struct {
+  int iterations;
+  double residual;          /* last ||r||_2                                               */
+  double initial_residual;
+  double chebyshev_max_eigenvalue, chebyshev_min_eigenvalue;
+  uint64_t operator_applications;
+} b200mf_solver_result;
+
+int b200mf_cg_solve(const b200mf_setup *s, const b200mf_operator *op,
+                    const b200mf_solver_desc *solver, void *x, const void *b,
+                    b200mf_solver_result *result, void *stream);
+/* x and b are HOST arrays of n_owned_dofs elements (copies inside).                      */
+int b200mf_cg_solve_host(const b200mf_setup *s, const b200mf_operator *op,
+                         const b200mf_solver_desc *solver, void *x_host, const void *b_host,
+                         b200mf_solver_result *result);
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic mesh + DoF generator (HOST).  Stands in for GridGenerator::hyper_cube +
+ * Triangulation::refine_global / subdivided_hyper_cube + DoFHandler::distribute_dofs
+ * (source/dofs/dof_handler_policy.cc:1676-1719) for the >=100 M-DoF runs the reference's
+ * host setup cannot hold; numbering is bit-identical to deal.II's (tests/test_mesh.py).
+ * ---------------------------------------------------------------------------------- */
+enum { B200MF_MESH_MORTON = 0, B200MF_MESH_LEXICOGRAPHIC = 1 };
+enum { B200MF_DEFORM_NONE = 0, B200MF_DEFORM_SINE = 1 };
+
+typedef struct {
+  int dim, degree;
+  int cells_per_direction; /* power of two for MORTON                                    */
+  int cell_order;          /* B200MF_MESH_*                                              */
+  double left, right;
+  int deformation;      /* B200MF_DEFORM_SINE: x += a * prod_d sin(pi (x_d-left)/(right-left)) e */
+  double deformation_amplitude;
+  int dirichlet_boundary;   /* 1 => collect boundary dofs as constrained                 */
+  int mark_constrained_l2g; /* 1 => set B200MF_L2G_CONSTRAINED bits (CPU-MF semantics)   */
+} b200mf_mesh_desc;
+
+typedef struct {
+  uint64_t n_cells, n_dofs, n_boundary_dofs;
+  int dofs_per_cell, vertices_per_cell, dim;
+  const uint32_t *local_to_global; /* [n_cells][dofs_per_cell], lexicographic           */
+  const double *cell_vertices;     /* [n_cells][2^dim][dim]                             */
+  const uint32_t *boundary_dofs;   /* sorted                                            */
+} b200mf_mesh_view;
+
+int b200mf_mesh_create(const b200mf_mesh_desc *desc, b200mf_mesh **out);
+int b200mf_mesh_view_get(const b200mf_mesh *m, b200mf_mesh_view *view);
+int b200mf_mesh_destroy(b200mf_mesh *m);
+/* Convenience: setup straight from a generated mesh. */
+int b200mf_setup_create_from_mesh(const b200mf_mesh *m, int number, b200mf_setup **out);
+
+/* ------------------------------------------------------------------------------------ */
+const char *b200mf_last_error(void);
+int b200mf_version(void);
+/* Number of engine kernels launched by this process so far (bench.py "gpu_launches"). */
+uint64_t b200mf_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MF_H */

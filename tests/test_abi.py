@@ -1,0 +1,59 @@
+"""The C-ABI library loads and exports every symbol include/b200mf.h declares; without a
+GPU every compute entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import dealii_b200
+from dealii_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200mf.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200mf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    lib = L.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in b200mf.h but not exported"
+        assert name in L.SYMBOLS, f"{name} has no ctypes prototype"
+    assert lib.b200mf_version() == 100
+
+
+def test_struct_layout_matches_header_sizes(tmp_path):
+    """sizeof() of every struct as gcc sees include/b200mf.h vs the ctypes mirrors."""
+    import subprocess
+    structs = {"b200mf_setup_desc": L.SetupDesc, "b200mf_setup_info": L.SetupInfo,
+               "b200mf_operator": L.Operator, "b200mf_solver_desc": L.SolverDesc,
+               "b200mf_solver_result": L.SolverResult, "b200mf_mesh_desc": L.MeshDesc,
+               "b200mf_mesh_view": L.MeshView}
+    src = tmp_path / "sizes.c"
+    body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in structs)
+    src.write_text('#include <stdio.h>\n#include "b200mf.h"\nint main(void){' + body + 'return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    sizes = dict(zip(out[0::2], map(int, out[1::2])))
+    for name, cls in structs.items():
+        assert sizes[name] == C.sizeof(cls), name
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    m = dealii_b200.HyperCubeMesh(3, 2, refinements=1)
+    with pytest.raises(dealii_b200.B200MFError) as e:
+        dealii_b200.MatrixFree().reinit_from_mesh(m)
+    assert e.value.code == L.ERR_CUDA
+    # the raw ABI call reports the same
+    h = C.c_void_p()
+    rc = L.load().b200mf_setup_create_from_mesh(m._h, L.F64, C.byref(h))
+    assert rc == L.ERR_CUDA and b"no CPU fallback" in L.load().b200mf_last_error()

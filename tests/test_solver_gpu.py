@@ -1,0 +1,96 @@
+"""CG / Jacobi / Chebyshev on the device vs the oracle (which reproduces the reference's
+golden step-64 output): iteration counts within +-1, solutions to solver tolerance."""
+import numpy as np
+import pytest
+import torch
+
+import dealii_b200
+from oracle import step64
+from oracle.solvers import DiagonalMatrix as ODiag, solver_cg
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = {1: (343, 10, "0.0205439"), 2: (2197, 14, "0.0205269"), 3: (15625, 29, "0.0205261")}
+
+
+def build(ref, number="f64"):
+    o, m = ref["oracle"], ref["oracle"].mesh
+    mf = dealii_b200.MatrixFree(number)
+    mf.reinit(m.dim, m.degree, m.l2g.astype(np.uint32), cell_vertices=m.cell_vertices,
+              constrained_dofs=m.boundary_dofs, n_owned_dofs=m.n_dofs)
+    coef = mf.evaluate_coefficients(step64.helmholtz_coefficient)
+    A = dealii_b200.HelmholtzOperator(mf, coef)
+    return mf, A
+
+
+@pytest.mark.parametrize("refinements", [1, 2, 3])
+def test_step64_chebyshev_cg_matches_golden(refinements):
+    """examples/step-64 (Q3): DoFs, CG iterations and solution norm of doc/results.dox."""
+    ref = step64.run_cycle(refinements)
+    n_dofs, its, norm = GOLDEN[refinements]
+    assert ref["n_dofs"] == n_dofs and ref["iterations"] == its
+    mf, A = build(ref)
+    inv_diag = A.compute_diagonal()
+    np.testing.assert_allclose(inv_diag.vector.cpu().numpy(), ref["inv_diag"], rtol=1e-12)
+    prec = dealii_b200.PreconditionChebyshev(degree=5, smoothing_range=15.0,
+                                             eig_cg_n_iterations=10, preconditioner=inv_diag)
+    b = torch.from_numpy(ref["b"]).cuda()
+    x = mf.initialize_dof_vector()
+    control = dealii_b200.SolverControl(n_dofs, 1e-12 * float(np.linalg.norm(ref["b"])))
+    res = dealii_b200.SolverCG(control).solve(A, x, b, prec)
+    assert abs(control.last_step() - its) <= 1
+    cheb = ref["chebyshev"].info
+    assert abs(res.chebyshev_max_eigenvalue - cheb["max_eigenvalue"]) < 1e-8 * cheb["max_eigenvalue"]
+    xs = x.cpu().numpy()
+    assert np.abs(xs - ref["x"]).max() < 1e-9 * np.abs(ref["x"]).max()
+    assert f"{step64.l2_norm_of_solution(ref['oracle'], xs):.6g}" == norm
+
+
+@pytest.mark.parametrize("prec_kind", ["jacobi", "none"])
+def test_cg_jacobi_and_identity_iteration_counts(prec_kind):
+    ref = step64.run_cycle(2, preconditioner=prec_kind)
+    mf, A = build(ref)
+    inv_diag = A.compute_diagonal()
+    b = torch.from_numpy(ref["b"]).cuda()
+    x = mf.initialize_dof_vector()
+    control = dealii_b200.SolverControl(5000, 1e-12 * float(np.linalg.norm(ref["b"])))
+    dealii_b200.SolverCG(control).solve(A, x, b, inv_diag if prec_kind == "jacobi" else None)
+    assert abs(control.last_step() - ref["iterations"]) <= 1
+    assert np.abs(x.cpu().numpy() - ref["x"]).max() < 1e-9 * np.abs(ref["x"]).max()
+
+
+def test_cg_nonzero_start_vector_and_host_entry_point():
+    ref = step64.run_cycle(1, preconditioner="jacobi")
+    mf, A = build(ref)
+    inv_diag = A.compute_diagonal()
+    o = ref["oracle"]
+    x0 = np.random.default_rng(0).random(o.mesh.n_dofs)
+    x0[o.mesh.boundary_dofs] = 0.0
+    tol = 1e-12 * float(np.linalg.norm(ref["b"]))
+    want = solver_cg(o.vmult, ref["b"], ODiag(ref["inv_diag"]), x0=x0, tol=tol, max_steps=1000)
+    x = torch.from_numpy(x0).cuda()
+    control = dealii_b200.SolverControl(1000, tol)
+    dealii_b200.SolverCG(control).solve(A, x, torch.from_numpy(ref["b"]).cuda(), inv_diag)
+    assert abs(control.last_step() - want["iterations"]) <= 1
+    assert np.abs(x.cpu().numpy() - want["x"]).max() < 1e-9 * np.abs(want["x"]).max()
+
+
+def test_no_convergence_is_reported():
+    ref = step64.run_cycle(2, preconditioner="none")
+    mf, A = build(ref)
+    x = mf.initialize_dof_vector()
+    control = dealii_b200.SolverControl(3, 1e-30)
+    with pytest.raises(dealii_b200.B200MFError) as e:
+        dealii_b200.SolverCG(control).solve(A, x, torch.from_numpy(ref["b"]).cuda(), None)
+    assert e.value.code == dealii_b200._lib.ERR_NOCONVERGENCE and control.last_step() == 3
+
+
+def test_cg_fp32():
+    ref = step64.run_cycle(1, preconditioner="jacobi")
+    mf, A = build(ref, "f32")
+    inv_diag = A.compute_diagonal()
+    b = torch.from_numpy(ref["b"].astype(np.float32)).cuda()
+    x = mf.initialize_dof_vector()
+    control = dealii_b200.SolverControl(1000, 1e-5 * float(np.linalg.norm(ref["b"])))
+    dealii_b200.SolverCG(control).solve(A, x, b, inv_diag)
+    assert np.abs(x.cpu().numpy() - ref["x"]).max() < 1e-4 * np.abs(ref["x"]).max()
