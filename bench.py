@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the matrix-free operator engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              # engine arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+Workload (BASELINE.json configs[1]): 3D Q4 Laplace vmult, FP64, affine Cartesian hyper_cube
+refined globally 7 times (128^3 cells, 513^3 = 135,005,697 DoFs) per GPU; a "step" is one
+vmult (dst = 0; cell loop; copy_constrained_values) over the whole mesh.  At N > 1 every rank
+owns its own sub-cube of that size (weak scaling, one process per GPU).
+
+One JSON line on stdout (rank 0), see the task contract: value = whole-job GDoF/s with the
+vectors resident in HBM, e2e = the same through the C-ABI host entry point
+(b200mf_vmult_host: pinned host src -> device -> vmult -> host dst inside the timed region),
+roofline = algorithmic bytes (16 B/DoF) of the cell-loop kernel over its
+CUDA-event duration against MEASURED_PEAKS.json, cpu_baseline = oracle/mf_cpu.c (the C
+restatement of the reference's vectorised CPU MatrixFree path) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vmult_throughput_3d_q4_laplace"
+UNIT = "GDoF/s"
+BYTES_PER_DOF = {"f64": 16.0, "f32": 8.0}            # read src + write dst
+CG_BYTES_PER_DOF = {"f64": 72.0, "f32": 36.0}        # fused Jacobi-CG iteration
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--refinements", type=int, default=7)
+    ap.add_argument("--number", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--deformation", type=float, default=0.0)
+    ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-refinements", type=int, default=6,
+                    help="per-core sub-cube of the CPU baseline sample")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.kill()          # the exact PID we started
+        self.proc.wait()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU reference
+def cpu_reference_sample(degree, refinements, steps, warmup, deformation=0.0):
+    """The reference's CPU MatrixFree path (C restatement oracle/mf_cpu.c) on every host core:
+    one independent single-rank instance per core on its own hyper_cube(refinements) -- the
+    only way the reference uses several cores without MPI/TBB (zero communication cost)."""
+    import numpy as np
+    import dealii_b200                       # host-side mesh generator only (no GPU work)
+    from oracle.mf_cpu import MatrixFreeCPU, time_vmult_on_cores
+    cores = len(os.sched_getaffinity(0))
+    mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements,
+                                     deformation_amplitude=deformation)
+    ops = [MatrixFreeCPU(3, degree, mesh.l2g, mesh.cell_vertices, mesh.n_dofs) for _ in range(cores)]
+    srcs = [np.random.default_rng(42 + i).random(mesh.n_dofs) for i in range(cores)]
+    t = time_vmult_on_cores(ops, srcs, steps, warmup=max(warmup, 1))
+    total = cores * mesh.n_dofs
+    return {"value": total * steps / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": (f"{cores} concurrent single-rank instances (1 per core) of oracle/mf_cpu.c, each "
+                       f"3D Q{degree} hyper_cube refine_global({refinements}) = {mesh.n_dofs} DoFs, "
+                       f"{steps} vmults after {max(warmup, 1)} warm-up; reference unbuildable here "
+                       f"(cmake), port follows matrix_free/evaluation_kernels.h:1835-1916"),
+            "seconds": t, "dofs_per_step": total}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    r = cpu_reference_sample(args.degree, args.cpu_refinements, steps, min(args.warmup, 3),
+                             args.deformation)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(min(args.warmup, 3), 1),
+            "ms_per_step": r["seconds"] / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, r["dofs_per_step"], "host cores only"),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_dofs_total, parallelism):
+    return {"workload": (f"3D Q{args.degree} Laplace vmult, {args.number}, "
+                         f"{'deformed (general cells)' if args.deformation else 'affine Cartesian'} "
+                         f"hyper_cube refine_global({args.refinements}) per GPU"),
+            "degree": args.degree, "dim": 3, "n_dofs_total": int(n_dofs_total),
+            "refinements": args.refinements, "parallelism": parallelism,
+            "l2": "inputs larger than L2 (vectors >= 1 GB each; no flush needed)"}
+
+
+# ----------------------------------------------------------------------------- engine arm
+def run_engine(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dealii_b200
+    from dealii_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- setup: every rank owns one hyper_cube(refinements) sub-domain
+    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements,
+                                     deformation_amplitude=args.deformation)
+    mf = dealii_b200.MatrixFree(args.number, dev).reinit_from_mesh(mesh)
+    op = dealii_b200.LaplaceOperator(mf)
+    n_dofs = mf.n_owned
+    n_total = n_dofs * world
+    tdt = mf.torch_dtype
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+    src = torch.rand(n_dofs, dtype=tdt, device=dev, generator=gen)
+    dst = mf.initialize_dof_vector()
+    launches0 = lib.b200mf_kernel_launch_count()
+
+    # ---- value: K vmults, vectors resident in HBM
+    for _ in range(max(args.warmup, 3)):
+        op.vmult(dst, src)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    lc0 = lib.b200mf_kernel_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        op.vmult(dst, src)
+    e1.record()
+    torch.cuda.synchronize()
+    lc1 = lib.b200mf_kernel_launch_count()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = n_total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline: the cell-loop kernel alone (CUDA events on its stream)
+    reps = max(args.steps, 10)
+    for _ in range(3):
+        mf.cell_loop(op.op, src, dst)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        mf.cell_loop(op.op, src, dst)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_kernel = e0.elapsed_time(e1) / reps
+    peak, peak_src = measured_peak()
+    bpd = BYTES_PER_DOF[args.number]
+    if args.deformation:
+        p = args.degree
+        bpd += 6 * (bpd / 2) * ((p + 1) / p) ** 3        # merged symmetric metric per q-point
+    achieved = bpd * n_dofs / (ms_kernel * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "kernel": "cell_loop_kernel<3,%d,%s>" % (args.degree + 1,
+                                                         "double" if args.number == "f64" else "float"),
+                "kernel_ms": ms_kernel, "algorithmic_bytes_per_dof": bpd, "peak_source": peak_src,
+                "note": ("FP64 sum factorisation is co-bound by the FP64 pipe (37.1 TFLOP/s measured, "
+                         "tools/fp64_peak.cu); see DESIGN.md")}
+
+    # ---- e2e: the C-ABI host entry point, host<->device copies inside the timed region
+    nbytes = n_dofs * (8 if args.number == "f64" else 4)
+    h_src = torch.empty(n_dofs, dtype=tdt).pin_memory()
+    h_dst = torch.empty(n_dofs, dtype=tdt).pin_memory()
+    h_src.copy_(src)
+    e2e_steps = max(2, min(args.steps, 5))
+    op.vmult_host(h_dst.numpy(), h_src.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        op.vmult_host(h_dst.numpy(), h_src.numpy())
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": n_total * e2e_steps / t_e2e / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+           "api": "b200mf_vmult_host (include/b200mf.h)"}
+    check = float((h_dst[:1000].to(dev) - dst[:1000]).abs().max())  # same result as device path
+    del h_src, h_dst
+
+    # ---- CG + Jacobi (the second half of the metric): DoF-iterations/s
+    cg = None
+    if not args.no_cg:
+        cg = run_cg(args, dev, rank, world, barrier, max_over_ranks, peak)
+
+    launches = lc1 - lc0
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del mesh
+        r = cpu_reference_sample(args.degree, args.cpu_refinements, 8, 1, args.deformation)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.number, "data": "synthetic",
+                "config": workload_config(args, n_total,
+                                          "1 GPU" if world == 1 else
+                                          f"{world} ranks, one sub-cube per GPU"),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "cg": cg,
+                "e2e_matches_device": check == 0.0}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cg(args, dev, rank, world, barrier, max_over_ranks, peak):
+    """SolverCG + Jacobi on the same mesh with zero Dirichlet boundary, rhs = 1: a fixed
+    number of iterations (the solve is stopped by max_iterations, like IterationNumberControl)."""
+    import torch
+    import dealii_b200
+    from dealii_b200 import _lib as L
+    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements,
+                                     deformation_amplitude=args.deformation, dirichlet_boundary=True)
+    mf = dealii_b200.MatrixFree(args.number, dev).reinit_from_mesh(mesh)
+    A = dealii_b200.LaplaceOperator(mf)
+    inv_diag = A.compute_diagonal()
+    b = torch.ones(mf.n_owned, dtype=mf.torch_dtype, device=dev)
+    mf.set_constrained_values(0.0, b)
+    iters = max(args.steps, 10)
+    best = None
+    for rep in range(2):                      # first solve = warm-up
+        x = mf.initialize_dof_vector()
+        control = dealii_b200.SolverControl(iters, 1e-300)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        try:
+            dealii_b200.SolverCG(control).solve(A, x, b, inv_diag)
+        except L.B200MFError as err:          # NoConvergence by construction
+            if err.code != L.ERR_NOCONVERGENCE:
+                raise
+        e1.record()
+        torch.cuda.synchronize()
+        best = max_over_ranks(e0.elapsed_time(e1))
+    its = control.last_step()
+    n_total = mf.n_owned * world
+    val = n_total * its / (best * 1e-3) / 1e9
+    bpd = CG_BYTES_PER_DOF[args.number]
+    return {"metric": "cg_jacobi_throughput", "value": val, "unit": "GDoF-iterations/s",
+            "iterations": its, "ms_per_iteration": best / max(its, 1), "residual": control.last_value(),
+            "roofline_frac": bpd * mf.n_owned * its / (best * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_dof_iteration": bpd}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)
