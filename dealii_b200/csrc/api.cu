@@ -422,7 +422,18 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     s.subface.assign(d->subface_interpolation_matrix, d->subface_interpolation_matrix + n * n);
 
   // --- indices
-  TRY(dev_alloc_copy<uint32_t>(&s.d_l2g, d->local_to_global, d->n_cells * nq, s, &s.index_bytes));
+  // the index list is padded with kL2gPadCells cells of "constrained" entries so that the
+  // plane kernel can copy whole cell groups past the last cell without bounds checks
+  {
+    const size_t real = (size_t)d->n_cells * nq, pad = (size_t)kL2gPadCells * nq;
+    B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_l2g, (real + pad) * sizeof(uint32_t)));
+    if (real)
+      B200MF_CUDA_CHECK(cudaMemcpy(s.d_l2g, d->local_to_global, real * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice));
+    B200MF_CUDA_CHECK(cudaMemset(s.d_l2g + real, 0xff, pad * sizeof(uint32_t)));
+    s.device_bytes += (real + pad) * sizeof(uint32_t);
+    s.index_bytes += (real + pad) * sizeof(uint32_t);
+  }
   if (d->constraint_mask) {
     for (uint64_t c = 0; c < d->n_cells; ++c)
       if (d->constraint_mask[c]) { s.any_mask = true; break; }

@@ -1,6 +1,10 @@
 // Instantiates the cell kernels for one value of n = degree + 1 (compile with -DB200MF_N=n);
 // the build compiles this file once per degree so the eight degrees build in parallel.
+#include <algorithm>
+#include <cstdlib>
+
 #include "cell_kernels.cuh"
+#include "cell_kernels_plane.cuh"
 
 #ifndef B200MF_N
 #error "compile with -DB200MF_N=<degree+1>"
@@ -42,6 +46,37 @@ int launch_one(const Setup &s, const b200mf_operator &op, void *dst, const void 
   const uint64_t n_cells = cell_end - cell_begin;
   const unsigned grid = (unsigned)((n_cells + Cfg::cells - 1) / Cfg::cells);
   size_t smem = sizeof(Number) * Cfg::smem_elems;
+  if constexpr (dim == 3 && n <= 6) {
+    // fast path: plane-per-thread kernel (cells without hanging-node masks)
+    static const bool force_v1 = [] {
+      const char *e = std::getenv("B200MF_KERNEL");
+      return e != nullptr && std::string(e) == "v1";
+    }();
+    if (!diagonal && p.mask == nullptr && !force_v1) {
+      using PCfg = PlaneCfg<n, Number>;
+      auto kernel = dot_accum != nullptr ? cell_loop_plane_kernel<n, Number, KIND, true>
+                                         : cell_loop_plane_kernel<n, Number, KIND, false>;
+      static int resident_ctas_v[2] = {0, 0}; // persistent grid: SMs x resident CTAs per SM
+      int &resident_ctas = resident_ctas_v[dot_accum != nullptr ? 1 : 0];
+      if (resident_ctas == 0) {
+        B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)PCfg::smem_bytes));
+        int dev = 0, sms = 0, per_sm = 0;
+        B200MF_CUDA_CHECK(cudaGetDevice(&dev));
+        B200MF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        B200MF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PCfg::threads,
+                                                                        PCfg::smem_bytes));
+        if (per_sm < 1) per_sm = 1;
+        resident_ctas = sms * per_sm;
+      }
+      const uint64_t needed = (n_cells + PCfg::cells - 1) / PCfg::cells;
+      const unsigned pgrid = (unsigned)std::min<uint64_t>(needed, (uint64_t)resident_ctas);
+      kernel<<<pgrid, PCfg::threads, PCfg::smem_bytes, stream>>>(p);
+      count_launch();
+      B200MF_CUDA_CHECK(cudaGetLastError());
+      return B200MF_OK;
+    }
+  }
   if (diagonal) {
     smem += sizeof(Number) * Cfg::cells * Cfg::npc;
     auto kernel = cell_diagonal_kernel<dim, n, Number, KIND>;

@@ -45,25 +45,18 @@ __device__ __forceinline__ void apply_eo(const EoMatrix<Number, n> &M, const Num
   }
 #pragma unroll
   for (int q = 0; q < hq; ++q) {
-    Number X = Number(0);
-    if (sym == 1) {
-      if (n % 2 == 1) X = M.mid[q] * in[h];
+    // accumulators start from a product (no zero-initialised registers)
+    const Number *xa = (sym == 1) ? xe : xo; // operand of the E block
+    const Number *xb = (sym == 1) ? xo : xe; // operand of the O block
+    Number X = M.E[q] * xa[0];
 #pragma unroll
-      for (int i = 0; i < h; ++i) X += M.E[i * hq + q] * xe[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < h; ++i) X += M.E[i * hq + q] * xo[i];
-    }
+    for (int i = 1; i < h; ++i) X += M.E[i * hq + q] * xa[i];
+    if (sym == 1 && n % 2 == 1) X += M.mid[q] * in[h];
     if (q < h) {
-      Number Y = Number(0);
-      if (sym == 1) {
+      Number Y = M.O[q] * xb[0];
 #pragma unroll
-        for (int i = 0; i < h; ++i) Y += M.O[i * h + q] * xo[i];
-      } else {
-        if (n % 2 == 1) Y = M.mid[q] * in[h];
-#pragma unroll
-        for (int i = 0; i < h; ++i) Y += M.O[i * h + q] * xe[i];
-      }
+      for (int i = 1; i < h; ++i) Y += M.O[i * h + q] * xb[i];
+      if (sym != 1 && n % 2 == 1) Y += M.mid[q] * in[h];
       out[q] = X + Y;
       out[n - 1 - q] = X - Y;
     } else {

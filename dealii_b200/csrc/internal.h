@@ -36,6 +36,7 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
   } while (0)
 
 constexpr int kMaxN = 9; // degree <= 8
+constexpr int kL2gPadCells = 16; // >= cells per warp of every plane-kernel configuration
 
 // Even-odd packed 1D matrix for out[q] = sum_i M[i][q] in[i] with
 // M[n-1-i][n-1-q] = +/- M[i][q]  (cf. shape_info.templates.h:1153-1180 convert_to_eo).
@@ -57,7 +58,9 @@ struct ShapeData {
   EoMatrix<Number, n> St; // quadrature points -> dofs
   EoMatrix<Number, n> D;  // collocation derivative (skew-symmetric)
   EoMatrix<Number, n> Dt;
+  EoMatrix<Number, n> DtW; // Dt with the quadrature weight of the input point folded in
   Number w[n];            // 1D quadrature weights
+  Number w2[n * n];       // w[a] * w[b] at [a * n + b]
 };
 
 // Host-side description of the operator passed to the kernels.

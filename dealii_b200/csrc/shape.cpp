@@ -160,7 +160,14 @@ void fill_shape_data(const Setup &s, ShapeData<Number, n> &out) {
   pack_eo<Number, n>(s.shape_values.data(), true, out.St);
   pack_eo<Number, n>(s.shape_grad_colloc.data(), false, out.D);
   pack_eo<Number, n>(s.shape_grad_colloc.data(), true, out.Dt);
+  // DtW: out[i] = sum_q (w[q] D[i][q]) in[q]; symmetric weights keep the skew structure
+  std::vector<double> dw(n * n);
+  for (int i = 0; i < n; ++i)
+    for (int q = 0; q < n; ++q) dw[i * n + q] = s.q_weights[q] * s.shape_grad_colloc[i * n + q];
+  pack_eo<Number, n>(dw.data(), true, out.DtW);
   for (int q = 0; q < n; ++q) out.w[q] = Number(s.q_weights[q]);
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) out.w2[a * n + b] = Number(s.q_weights[a] * s.q_weights[b]);
 }
 
 #define INST(N)                                                                     \
