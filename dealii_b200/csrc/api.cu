@@ -113,7 +113,7 @@ __device__ inline double invert(const double J[dim][dim], double Ji[dim][dim]) {
   }
 }
 
-// metric[cell][s][q] = w_q det(J) (J^-1 J^-T)_s (s over the upper triangle), jxw[cell][q]
+// metric (layout: metric_offset) = w_q det(J) (J^-1 J^-T)_s (s over the upper triangle), jxw[cell][q]
 template <int dim, typename Number>
 __global__ void general_geometry_from_vertices(const double *vertices, const double *qp1d,
                                                const double *qw1d, int n, uint64_t n_cells,
@@ -136,7 +136,7 @@ __global__ void general_geometry_from_vertices(const double *vertices, const dou
     for (int f = e; f < dim; ++f, ++s) {
       double m = 0.0;
       for (int d = 0; d < dim; ++d) m += Ji[e][d] * Ji[f][d];
-      metric[cell * (NS * nq) + s * nq + q] = Number(m * det * w);
+      metric[metric_offset<dim>(n, cell, s, q)] = Number(m * det * w);
     }
   jxw[cell * nq + q] = Number(det * w);
 }
@@ -144,8 +144,8 @@ __global__ void general_geometry_from_vertices(const double *vertices, const dou
 // same from the arrays Portable::MatrixFree stores (inv_jacobian(q,cell,d,e), JxW(q,cell))
 template <int dim, typename Number>
 __global__ void general_geometry_from_jacobians(const double *inv_jac, const double *jxw_in,
-                                                int nq, uint64_t n_cells, Number *metric,
-                                                Number *jxw) {
+                                                int nq, int n1d, uint64_t n_cells,
+                                                Number *metric, Number *jxw) {
   constexpr int NS = dim * (dim + 1) / 2;
   const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_cells * nq) return;
@@ -158,7 +158,7 @@ __global__ void general_geometry_from_jacobians(const double *inv_jac, const dou
     for (int f = e; f < dim; ++f, ++s) {
       double m = 0.0;
       for (int d = 0; d < dim; ++d) m += Ji[e * dim + d] * Ji[f * dim + d];
-      metric[cell * (NS * nq) + s * nq + q] = Number(m * jw);
+      metric[metric_offset<dim>(n1d, cell, s, q)] = Number(m * jw);
     }
   jxw[cell * nq + q] = Number(jw);
 }
@@ -176,6 +176,17 @@ __global__ void quadrature_points_kernel(const double *vertices, const double *q
   for (int d = 0; d < dim; ++d) xi[d] = qp1d[qi[d]];
   q1_jacobian<dim>(vertices + cell * (1 << dim) * dim, xi, J, x);
   for (int d = 0; d < dim; ++d) out[gid * dim + d] = x[d];
+}
+
+// entries flagged B200MF_L2G_CONSTRAINED whose index part is out of range (e.g. deal.II's
+// numbers::invalid_unsigned_int) are redirected to index 0 so that the branch-free kernels
+// may form the address of every entry
+__global__ void sanitize_l2g_kernel(uint32_t *l2g, uint64_t count, uint32_t n_local) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t v = l2g[i];
+  if ((v & B200MF_L2G_CONSTRAINED) && (v & ~B200MF_L2G_CONSTRAINED) >= n_local)
+    l2g[i] = B200MF_L2G_CONSTRAINED;
 }
 
 template <typename Number>
@@ -430,7 +441,18 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     if (real)
       B200MF_CUDA_CHECK(cudaMemcpy(s.d_l2g, d->local_to_global, real * sizeof(uint32_t),
                                    cudaMemcpyHostToDevice));
-    B200MF_CUDA_CHECK(cudaMemset(s.d_l2g + real, 0xff, pad * sizeof(uint32_t)));
+    {
+      // padding entries: "constrained" marker on index 0 (read as 0, scatter adds 0 to dst[0])
+      std::vector<uint32_t> padv(pad, B200MF_L2G_CONSTRAINED);
+      B200MF_CUDA_CHECK(cudaMemcpy(s.d_l2g + real, padv.data(), pad * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice));
+    }
+    if (real) {
+      sanitize_l2g_kernel<<<(unsigned)((real + 255) / 256), 256>>>(
+          s.d_l2g, real, (uint32_t)(d->n_owned_dofs + d->n_ghost_dofs));
+      count_launch();
+      B200MF_CUDA_CHECK(cudaGetLastError());
+    }
     s.device_bytes += (real + pad) * sizeof(uint32_t);
     s.index_bytes += (real + pad) * sizeof(uint32_t);
   }
@@ -506,13 +528,13 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     s.geometry_bytes += total_q * (NS + 1) * ns;
     if (total_q) {
       if (s.dim == 2 && s.number == B200MF_F64)
-        general_geometry_from_jacobians<2, double><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+        general_geometry_from_jacobians<2, double><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
       else if (s.dim == 2)
-        general_geometry_from_jacobians<2, float><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+        general_geometry_from_jacobians<2, float><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
       else if (s.number == B200MF_F64)
-        general_geometry_from_jacobians<3, double><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+        general_geometry_from_jacobians<3, double><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
       else
-        general_geometry_from_jacobians<3, float><<<blocks, 256>>>(d_ij, d_jw, nq, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+        general_geometry_from_jacobians<3, float><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
       count_launch();
     }
     B200MF_CUDA_CHECK(cudaDeviceSynchronize());

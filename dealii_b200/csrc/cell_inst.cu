@@ -48,11 +48,21 @@ int launch_one(const Setup &s, const b200mf_operator &op, void *dst, const void 
   size_t smem = sizeof(Number) * Cfg::smem_elems;
   if constexpr (dim == 3 && n <= 6) {
     // fast path: plane-per-thread kernel (cells without hanging-node masks)
-    static const bool force_v1 = [] {
+    // kernel choice by measurement (profiles/r01_kernel_choice.txt): the plane kernel wins
+    // wherever its register planes fit; B200MF_KERNEL=v1|plane overrides for A/B runs
+    static const int forced = [] {
       const char *e = std::getenv("B200MF_KERNEL");
-      return e != nullptr && std::string(e) == "v1";
+      if (e == nullptr) return 0;
+      return std::string(e) == "v1" ? 1 : (std::string(e) == "plane" ? 2 : 0);
     }();
-    if (!diagonal && p.mask == nullptr && !force_v1) {
+    bool use_plane;
+    if (KIND == B200MF_CELLS_GENERAL)
+      use_plane = sizeof(Number) == 8 ? (n <= 4) : (n <= 3 || n == 5);
+    else
+      use_plane = n <= 5;
+    if (forced == 1) use_plane = false;
+    if (forced == 2) use_plane = true;
+    if (!diagonal && p.mask == nullptr && use_plane) {
       using PCfg = PlaneCfg<n, Number>;
       auto kernel = dot_accum != nullptr ? cell_loop_plane_kernel<n, Number, KIND, true>
                                          : cell_loop_plane_kernel<n, Number, KIND, false>;

@@ -161,9 +161,8 @@ __device__ __forceinline__ void quadrature_point_operation(
     for (int d = 0; d < dim; ++d) g[d] = G[d * npc + q];
     Number jxw;
     if (KIND == B200MF_CELLS_GENERAL) {
-      const Number *mq = p.metric + cell * (NS * npc) + q;
 #pragma unroll
-      for (int d = 0; d < NS; ++d) m[d] = mq[d * npc];
+      for (int d = 0; d < NS; ++d) m[d] = p.metric[metric_offset<dim>(n, cell, d, q)];
       jxw = has_mass ? p.jxw[gq] : Number(0);
     } else {
       const Number wq = wline * p.shape.w[k];

@@ -48,7 +48,7 @@ struct PlaneCfg {
   static constexpr size_t ibuf_bytes = ((sizeof(uint32_t) * (gdofs + 1) + 15) / 16) * 16;
   static constexpr size_t warp_bytes = 3 * (sizeof(Number) * buf + ibuf_bytes);
   static constexpr size_t table_bytes = ((sizeof(uint16_t) * (gdofs + 2) + 15) / 16) * 16;
-  static constexpr int warps_fit = (int)((220 * 1024 - table_bytes) / warp_bytes);
+  static constexpr int warps_fit = (int)((226 * 1024 - table_bytes) / warp_bytes);
   static constexpr int warps = warps_fit > 8 ? 8 : warps_fit;          // one CTA per SM
   static constexpr int threads = 32 * warps;
   static constexpr int cells = cpw * warps;                            // cells per CTA and pass
@@ -82,6 +82,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void prefetch_l2(const void *ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
+
+template <typename Number> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
 
 // in-register sweep over a plane a[i][j]: along j (ROWS) or along i (!ROWS)
 template <int n, int sym, bool ROWS, typename Number>
@@ -167,21 +171,43 @@ cell_loop_plane_kernel(const __grid_constant__ CellKernelParams<3, n, Number, KI
   // stage 2: read_dof_values of a group -- one asynchronous copy per dof from src into the
   // padded plane layout of data buffer U (constrained / padding entries are zero-filled)
   auto issue_gather = [&](Number *U, const uint32_t *I) {
+    uint2 i2[Cfg::gather_iters];
+    unsigned tb[Cfg::gather_iters];
 #pragma unroll
-    for (int k = 0; k < Cfg::gather_iters; ++k) {
+    for (int k = 0; k < Cfg::gather_iters; ++k) { // all shared-memory reads first ...
       const int e = 2 * (rank + Cfg::nact * k);
       if (k + 1 < Cfg::gather_iters || e < Cfg::gdofs) {
-        const uint2 i2 = *reinterpret_cast<const uint2 *>(I + e);
-        const unsigned tb = *reinterpret_cast<const unsigned *>(table + e);
-        const bool z0 = (i2.x & CBIT) != 0, z1 = (i2.y & CBIT) != 0;
-        cp_async_zfill(U + (tb & 0xffffu), p.src + (z0 ? 0u : i2.x), sizeof(Number), z0);
+        i2[k] = *reinterpret_cast<const uint2 *>(I + e);
+        tb[k] = *reinterpret_cast<const unsigned *>(table + e);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < Cfg::gather_iters; ++k) { // ... then the asynchronous copies
+      const int e = 2 * (rank + Cfg::nact * k);
+      if (k + 1 < Cfg::gather_iters || e < Cfg::gdofs) {
+        const bool z0 = (i2[k].x & CBIT) != 0, z1 = (i2[k].y & CBIT) != 0;
+        cp_async_zfill(U + (tb[k] & 0xffffu), p.src + (i2[k].x & ~CBIT), sizeof(Number), z0);
         if (Cfg::gdofs % 2 == 0 || e + 1 < Cfg::gdofs)
-          cp_async_zfill(U + (tb >> 16), p.src + (z1 ? 0u : i2.y), sizeof(Number), z1);
+          cp_async_zfill(U + (tb[k] >> 16), p.src + (i2[k].y & ~CBIT), sizeof(Number), z1);
       }
     }
   };
   auto dbuf = [&](int i) { return wbuf + i * Cfg::buf; };
   auto ibuf = [&](int i) { return reinterpret_cast<uint32_t *>(ibase + i * Cfg::ibuf_bytes); };
+
+  // metric of the (very common) single-geometry mesh: loaded once
+  Number m0[NS], det0 = Number(1);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) m0[s] = Number(0);
+  if (KIND != B200MF_CELLS_GENERAL && p.geom_id == nullptr) {
+    if (KIND == B200MF_CELLS_CARTESIAN) {
+      m0[0] = p.geom_table[0]; m0[1] = p.geom_table[1]; m0[2] = p.geom_table[2]; det0 = p.geom_table[3];
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) m0[s] = p.geom_table[s];
+      det0 = p.geom_table[NS];
+    }
+  }
 
   // pipeline prologue
   int rot = 0; // B0 = dbuf(rot), B1 = dbuf(rot+1), next gather -> dbuf(rot+2); same for ibuf
@@ -233,11 +259,11 @@ cell_loop_plane_kernel(const __grid_constant__ CellKernelParams<3, n, Number, KI
 
     // per-cell metric (Cartesian: diagonal of JxW J^-1 J^-T / w; affine: upper triangle)
     Number m[NS];
-    Number det = Number(1);
+    Number det = det0;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) m[s] = Number(0);
-    if (KIND != B200MF_CELLS_GENERAL) {
-      const unsigned gi = p.geom_id ? p.geom_id[cell] : 0u;
+    for (int s = 0; s < NS; ++s) m[s] = m0[s];
+    if (KIND != B200MF_CELLS_GENERAL && p.geom_id != nullptr) {
+      const unsigned gi = p.geom_id[cell];
       if (KIND == B200MF_CELLS_CARTESIAN) {
         const Number *tb = p.geom_table + gi * 4;
         m[0] = tb[0]; m[1] = tb[1]; m[2] = tb[2]; det = tb[3];
@@ -414,6 +440,19 @@ cell_loop_plane_kernel(const __grid_constant__ CellKernelParams<3, n, Number, KI
           for (int x = 0; x < n; ++x) Bz0[y + n * x] = u[y][x];
       }
       __syncwarp(MASK);
+      // metric rows of this thread's z-plane (layout metric_offset: [cell][z][y][s][x]) are
+      // streamed through registers one row ahead of their use, with wide loads
+      using V2 = typename Vec2<Number>::type;
+      constexpr int RV = 3 * n; // 6n numbers per row = 3n two-element vectors
+      V2 mrow[2][RV];
+      const V2 *mbase = (KIND == B200MF_CELLS_GENERAL)
+                            ? reinterpret_cast<const V2 *>(p.metric + ((cell * n + t) * n) * (NS * n))
+                            : nullptr;
+      auto load_row = [&](int y, V2 (&dst)[RV]) {
+#pragma unroll
+        for (int i = 0; i < RV; ++i) dst[i] = __ldg(mbase + y * RV + i);
+      };
+      if (KIND == B200MF_CELLS_GENERAL) load_row(0, mrow[0]);
       // ---- phase Y2: reference z-derivative -> B1
 #pragma unroll
       for (int x = 0; x < n; ++x) {
@@ -431,10 +470,11 @@ cell_loop_plane_kernel(const __grid_constant__ CellKernelParams<3, n, Number, KI
         const unsigned long long q0 = cell * npc + t * n2;
         const Number *gc = p.op.grad_coef ? p.op.grad_coef + q0 : nullptr;
         const Number *mc = p.op.mass_coef ? p.op.mass_coef + q0 : nullptr;
-        const Number *mq = (KIND == B200MF_CELLS_GENERAL) ? p.metric + cell * (NS * npc) + t * n2 : nullptr;
 #pragma unroll
         for (int y = 0; y < n; ++y) {
           Number hx[n], o[n];
+          if (KIND == B200MF_CELLS_GENERAL && y + 1 < n) load_row(y + 1, mrow[(y + 1) & 1]);
+          const Number *mr = reinterpret_cast<const Number *>(mrow[y & 1]); // [s][x]
 #pragma unroll
           for (int x = 0; x < n; ++x) {
             const Number gz = Bz1[y + n * x];
@@ -443,7 +483,7 @@ cell_loop_plane_kernel(const __grid_constant__ CellKernelParams<3, n, Number, KI
             Number jxw;
             if (KIND == B200MF_CELLS_GENERAL) {
 #pragma unroll
-              for (int s = 0; s < NS; ++s) m[s] = __ldg(mq + s * npc + y * n + x);
+              for (int s = 0; s < NS; ++s) m[s] = mr[s * n + x];
               jxw = has_mass ? p.jxw[q0 + y * n + x] : Number(0);
             } else {
               const Number wq = wt * sh.w2[y * n + x];
@@ -517,15 +557,19 @@ cell_loop_plane_kernel(const __grid_constant__ CellKernelParams<3, n, Number, KI
 #pragma unroll
         for (int x = 0; x < n; ++x) u[y][x] = Bz0[y + n * x];
       plane_sweep<n, 1, false>(sh.St, u);
-      if (valid) {
+      // branch-free: constrained / padding / out-of-range entries add 0 to a valid address
+      uint32_t idx[n][n];
 #pragma unroll
-        for (int y = 0; y < n; ++y)
+      for (int y = 0; y < n; ++y)
 #pragma unroll
-          for (int x = 0; x < n; ++x) {
-            const uint32_t idx = I0[y * n + x];
-            if (!(idx & CBIT)) atomicAdd(p.dst + idx, u[y][x]);
-          }
-      }
+        for (int x = 0; x < n; ++x) idx[y][x] = I0[y * n + x];
+#pragma unroll
+      for (int y = 0; y < n; ++y)
+#pragma unroll
+        for (int x = 0; x < n; ++x) {
+          const bool live = valid && !(idx[y][x] & CBIT);
+          atomicAdd(p.dst + (idx[y][x] & ~CBIT), live ? u[y][x] : Number(0));
+        }
     }
     if (DOT && valid) dot += dit;
     __syncwarp(MASK); // all reads of this iteration done before the buffers rotate

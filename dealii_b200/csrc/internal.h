@@ -63,6 +63,18 @@ struct ShapeData {
   Number w2[n * n];       // w[a] * w[b] at [a * n + b]
 };
 
+// Layout of the merged metric of general cells: rows of n quadrature points along x hold
+// their NS = dim(dim+1)/2 tensor entries next to each other,
+//   3D: [cell][z][y][s][x]      2D: [cell][y][s][x]
+// so that a thread reads the 6n (3n) numbers of one row with wide, fully used loads.
+template <int dim>
+__host__ __device__ inline unsigned long long metric_offset(int n, unsigned long long cell, int s,
+                                                            int q) {
+  constexpr int NS = dim * (dim + 1) / 2;
+  const int x = q % n, rest = q / n; // rest = y (2D) or y + n z (3D)
+  return ((cell * (unsigned long long)(dim == 2 ? n : n * n) + rest) * NS + s) * n + x;
+}
+
 // Host-side description of the operator passed to the kernels.
 template <typename Number>
 struct OperatorArgs {
