@@ -16,6 +16,7 @@ CELLS_CARTESIAN, CELLS_AFFINE, CELLS_GENERAL = 0, 1, 2
 L2G_CONSTRAINED = 0x80000000
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_CHEBYSHEV = 0, 1, 2
 MESH_MORTON, MESH_LEXICOGRAPHIC = 0, 1
+GHOSTS_RELEVANT, GHOSTS_TOUCHED = 0, 1
 DEFORM_NONE, DEFORM_SINE = 0, 1
 
 u64, u32p, u16p, f64p, vp = C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint16), C.POINTER(C.c_double), C.c_void_p
@@ -65,6 +66,18 @@ class MeshDesc(C.Structure):
                 ("dirichlet_boundary", C.c_int), ("mark_constrained_l2g", C.c_int)]
 
 
+class PartitionDesc(C.Structure):
+    _fields_ = [("mesh", MeshDesc), ("coarse", C.c_int * 3), ("n_ranks", C.c_int), ("rank", C.c_int),
+                ("ghost_mode", C.c_int), ("want_lattice_ids", C.c_int)]
+
+
+class PartitionView(C.Structure):
+    _fields_ = [("n_global_dofs", u64), ("n_global_cells", u64), ("first_owned_global", u64),
+                ("n_owned", u64), ("n_ghost", u64), ("n_cells_interior", u64),
+                ("rank_offsets", C.POINTER(u64)), ("ghost_global", C.POINTER(u64)),
+                ("lattice_ids", C.POINTER(u64))]
+
+
 class MeshView(C.Structure):
     _fields_ = [("n_cells", u64), ("n_dofs", u64), ("n_boundary_dofs", u64),
                 ("dofs_per_cell", C.c_int), ("vertices_per_cell", C.c_int), ("dim", C.c_int),
@@ -93,6 +106,17 @@ SYMBOLS = {
     "b200mf_cg_solve_host": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
                                        C.POINTER(SolverResult)]),
     "b200mf_mesh_create": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(vp)]),
+    "b200mf_mesh_create_partitioned": (C.c_int, [C.POINTER(PartitionDesc), C.POINTER(vp)]),
+    "b200mf_mesh_partition_view_get": (C.c_int, [vp, C.POINTER(PartitionView)]),
+    "b200mf_cell_loop_range": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp]),
+    "b200mf_cell_loop_range_dot": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),
+    "b200mf_copy_constrained_values_dot": (C.c_int, [vp, vp, vp, vp, vp]),
+    "b200mf_cg_init": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, u64, vp, vp]),
+    "b200mf_cg_post": (C.c_int, [C.c_int, vp, vp, vp, u64, vp, C.c_int, vp]),
+    "b200mf_cg_pre": (C.c_int, [C.c_int, vp, vp, vp, vp, u64, vp, C.c_int, vp]),
+    "b200mf_cg_final": (C.c_int, [C.c_int, vp, vp, u64, vp, C.c_int, vp]),
+    "b200mf_ghost_pack": (C.c_int, [C.c_int, vp, vp, vp, u64, vp]),
+    "b200mf_ghost_unpack_add": (C.c_int, [C.c_int, vp, vp, vp, u64, vp]),
     "b200mf_mesh_view_get": (C.c_int, [vp, C.POINTER(MeshView)]),
     "b200mf_mesh_destroy": (C.c_int, [vp]),
     "b200mf_setup_create_from_mesh": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),

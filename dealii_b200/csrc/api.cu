@@ -119,7 +119,6 @@ __global__ void general_geometry_from_vertices(const double *vertices, const dou
                                                const double *qw1d, int n, uint64_t n_cells,
                                                Number *metric, Number *jxw) {
   const int nq = dim == 2 ? n * n : n * n * n;
-  constexpr int NS = dim * (dim + 1) / 2;
   const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_cells * nq) return;
   const uint64_t cell = gid / nq;
@@ -146,7 +145,6 @@ template <int dim, typename Number>
 __global__ void general_geometry_from_jacobians(const double *inv_jac, const double *jxw_in,
                                                 int nq, int n1d, uint64_t n_cells,
                                                 Number *metric, Number *jxw) {
-  constexpr int NS = dim * (dim + 1) / 2;
   const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_cells * nq) return;
   const uint64_t cell = gid / nq;
@@ -607,6 +605,27 @@ int b200mf_cell_loop(const b200mf_setup *h, const b200mf_operator *op, void *dst
                      void *stream) {
   B200MF_REQUIRE(h && op && dst && src, "null argument");
   return launch_cell_loop(h->impl, *op, dst, src, 0, h->impl.n_cells, (cudaStream_t)stream, nullptr);
+}
+
+int b200mf_cell_loop_range(const b200mf_setup *h, const b200mf_operator *op, void *dst,
+                           const void *src, uint64_t cell_begin, uint64_t cell_end, void *stream) {
+  B200MF_REQUIRE(h && op && dst && src, "null argument");
+  B200MF_REQUIRE(cell_begin <= cell_end && cell_end <= h->impl.n_cells, "bad cell range");
+  return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream, nullptr);
+}
+
+int b200mf_cell_loop_range_dot(const b200mf_setup *h, const b200mf_operator *op, void *dst,
+                               const void *src, uint64_t cell_begin, uint64_t cell_end,
+                               double *dot_accum, void *stream) {
+  B200MF_REQUIRE(h && op && dst && src, "null argument");
+  B200MF_REQUIRE(cell_begin <= cell_end && cell_end <= h->impl.n_cells, "bad cell range");
+  return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream, dot_accum);
+}
+
+int b200mf_copy_constrained_values_dot(const b200mf_setup *h, void *dst, const void *src,
+                                       double *dot_accum, void *stream) {
+  B200MF_REQUIRE(h && dst && src, "null argument");
+  return copy_constrained_impl(h->impl, dst, src, (cudaStream_t)stream, dot_accum);
 }
 
 int b200mf_copy_constrained_values(const b200mf_setup *h, void *dst, const void *src,

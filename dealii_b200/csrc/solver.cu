@@ -513,6 +513,54 @@ int b200mf_cg_solve(const b200mf_setup *h, const b200mf_operator *op,
   return solve_impl<float>(s, *op, *solver, x, b, result, (cudaStream_t)stream);
 }
 
+/* ---- building blocks of the fused CG for callers that interleave their own communication
+ * (multi-GPU: one all-reduce of the scalar slots between the kernels).  `scratch` is a
+ * caller-owned, zero-initialised device array of 24 doubles: slot(k) = scratch + 8*(k%3)
+ * holds [p.Ap, r.r, r.z] of iteration k. */
+#define B200MF_DISPATCH_NUMBER(number, CALL)                      \
+  do {                                                            \
+    if ((number) == B200MF_F64) { using T = double; CALL; }       \
+    else if ((number) == B200MF_F32) { using T = float; CALL; }   \
+    else { set_error("bad number type"); return B200MF_ERR_INVALID; } \
+  } while (0)
+
+int b200mf_cg_init(int number, void *r, void *p, const void *b, const void *Ax, const void *d,
+                   uint64_t n, double *scratch, void *stream) {
+  B200MF_REQUIRE(r && p && b && scratch, "null argument");
+  B200MF_DISPATCH_NUMBER(number, (cg_init_kernel<T><<<vec_grid(n), kVecThreads, 0, (cudaStream_t)stream>>>(
+      (T *)r, (T *)p, (const T *)b, (const T *)Ax, (const T *)d, n, scratch)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+int b200mf_cg_post(int number, void *r, const void *v, const void *d, uint64_t n, double *scratch,
+                   int it, void *stream) {
+  B200MF_REQUIRE(r && v && scratch, "null argument");
+  B200MF_DISPATCH_NUMBER(number, (cg_post_kernel<T><<<vec_grid(n), kVecThreads, 0, (cudaStream_t)stream>>>(
+      (T *)r, (const T *)v, (const T *)d, n, scratch, it)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+int b200mf_cg_pre(int number, void *x, void *p, const void *r, const void *d, uint64_t n,
+                  double *scratch, int it, void *stream) {
+  B200MF_REQUIRE(x && p && r && scratch, "null argument");
+  B200MF_DISPATCH_NUMBER(number, (cg_pre_kernel<T><<<vec_grid(n), kVecThreads, 0, (cudaStream_t)stream>>>(
+      (T *)x, (T *)p, (const T *)r, (const T *)d, n, scratch, it)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+int b200mf_cg_final(int number, void *x, const void *p, uint64_t n, const double *scratch, int it,
+                    void *stream) {
+  B200MF_REQUIRE(x && p && scratch, "null argument");
+  B200MF_DISPATCH_NUMBER(number, (cg_final_kernel<T><<<vec_grid(n), kVecThreads, 0, (cudaStream_t)stream>>>(
+      (T *)x, (const T *)p, n, scratch, it)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
 int b200mf_cg_solve_host(const b200mf_setup *h, const b200mf_operator *op,
                          const b200mf_solver_desc *solver, void *x_host, const void *b_host,
                          b200mf_solver_result *result) {

@@ -32,6 +32,21 @@ __global__ void dot_kernel(const Number *x, const Number *y, uint64_t n, double 
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
+// ghost exchange pack / unpack (base/partitioner.templates.h:119-137 and :604-671)
+template <typename Number>
+__global__ void pack_kernel(Number *buf, const Number *vec, const uint32_t *idx, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    buf[i] = vec[idx[i]];
+}
+template <typename Number>
+__global__ void unpack_add_kernel(Number *vec, const Number *buf, const uint32_t *idx, uint64_t n) {
+  // an owned dof can be imported from several neighbours: atomics
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    atomicAdd(vec + idx[i], buf[i]);
+}
+
 template <typename Number>
 int dot_impl(const void *x, const void *y, uint64_t n, double *result_host, cudaStream_t st) {
   double *d_out = nullptr;
@@ -100,6 +115,32 @@ int b200mf_vec_dot(int number, const void *x, const void *y, uint64_t n, double 
   if (number == B200MF_F32) return dot_impl<float>(x, y, n, result_host, (cudaStream_t)stream);
   set_error("bad number type");
   return B200MF_ERR_INVALID;
+}
+
+int b200mf_ghost_pack(int number, void *buf, const void *vec, const uint32_t *idx, uint64_t n,
+                      void *stream) {
+  if (n == 0) return B200MF_OK;
+  B200MF_REQUIRE(buf && vec && idx, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(number,
+           (pack_kernel<double><<<vec_grid(n), kVecThreads, 0, st>>>((double *)buf, (const double *)vec, idx, n)),
+           (pack_kernel<float><<<vec_grid(n), kVecThreads, 0, st>>>((float *)buf, (const float *)vec, idx, n)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+int b200mf_ghost_unpack_add(int number, void *vec, const void *buf, const uint32_t *idx, uint64_t n,
+                            void *stream) {
+  if (n == 0) return B200MF_OK;
+  B200MF_REQUIRE(buf && vec && idx, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(number,
+           (unpack_add_kernel<double><<<vec_grid(n), kVecThreads, 0, st>>>((double *)vec, (const double *)buf, idx, n)),
+           (unpack_add_kernel<float><<<vec_grid(n), kVecThreads, 0, st>>>((float *)vec, (const float *)buf, idx, n)));
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
 }
 
 } // extern "C"

@@ -1,0 +1,352 @@
+"""Multi-GPU layer of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+Mirrors, by name and meaning:
+  Partitioner            Utilities::MPI::Partitioner (base/partitioner.h:199; index algebra of
+                         source/base/partitioner.cc:185-330): owned range + sorted ghost indices
+                         -> ghost_targets, import_targets, import_indices
+  GhostExchange          LA::d::Vector::update_ghost_values_start/finish, compress_start/finish,
+                         zero_out_ghost_values (lac/la_parallel_vector.templates.h:1026-1332)
+  DistributedMatrixFree  Portable::MatrixFree::distributed_cell_loop with
+                         overlap_communication_computation
+                         (matrix_free/portable_matrix_free.templates.h:1567-1690)
+  solve_cg               SolverCG::solve (lac/solver_cg.h:1391) on distributed vectors: the fused
+                         device kernels of the C ABI with one all-reduce of the scalar slots
+                         where the reference calls MPI_Allreduce (lac/solver_cg.h:890-893)
+
+Pack / unpack-add, the operator and the CG vector updates are CUDA kernels of libb200mf.so;
+transport is NCCL point-to-point (ncclSend/ncclRecv grouped per exchange) over NVLink, issued
+on a side stream so that interior cells run while the ghost values are in flight.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .matrix_free import HyperCubeMesh, MatrixFree, _npptr, _ptr
+
+
+class PartitionedHyperCubeMesh(HyperCubeMesh):
+    """This rank's part of hyper_cube / subdivided_hyper_rectangle(coarse) refined globally,
+    partitioned and numbered like parallel::distributed::Triangulation + DoFHandler
+    (b200mf_mesh_create_partitioned)."""
+
+    def __init__(self, dim, degree, refinements, n_ranks, rank, coarse=(1, 1, 1), left=0.0, right=1.0,
+                 deformation_amplitude=0.0, dirichlet_boundary=False, mark_constrained_l2g=False,
+                 ghost_mode="relevant", want_lattice_ids=False):
+        lib = L.load()
+        d = L.PartitionDesc()
+        m = d.mesh
+        m.dim, m.degree = dim, degree
+        m.cells_per_direction, m.cell_order = 2 ** refinements, L.MESH_MORTON
+        m.left, m.right = left, right
+        m.deformation = L.DEFORM_SINE if deformation_amplitude != 0.0 else L.DEFORM_NONE
+        m.deformation_amplitude = deformation_amplitude
+        m.dirichlet_boundary = int(dirichlet_boundary)
+        m.mark_constrained_l2g = int(mark_constrained_l2g)
+        for k in range(3):
+            d.coarse[k] = coarse[k] if k < len(coarse) else 1
+        d.n_ranks, d.rank = n_ranks, rank
+        d.ghost_mode = L.GHOSTS_RELEVANT if ghost_mode == "relevant" else L.GHOSTS_TOUCHED
+        d.want_lattice_ids = int(want_lattice_ids)
+        self._h = C.c_void_p()
+        L.check(lib.b200mf_mesh_create_partitioned(C.byref(d), C.byref(self._h)))
+        v = L.MeshView()
+        L.check(lib.b200mf_mesh_view_get(self._h, C.byref(v)))
+        pv = L.PartitionView()
+        L.check(lib.b200mf_mesh_partition_view_get(self._h, C.byref(pv)))
+        self.dim, self.degree = dim, degree
+        self.n_cells, self.n_dofs = int(v.n_cells), int(v.n_dofs)
+        self.dofs_per_cell = int(v.dofs_per_cell)
+        self._view = v
+        self.n_ranks, self.rank = n_ranks, rank
+        self.n_owned, self.n_ghost = int(pv.n_owned), int(pv.n_ghost)
+        self.n_global_dofs, self.n_global_cells = int(pv.n_global_dofs), int(pv.n_global_cells)
+        self.first_owned_global = int(pv.first_owned_global)
+        self.n_cells_interior = int(pv.n_cells_interior)
+        self.rank_offsets = np.ctypeslib.as_array(pv.rank_offsets, shape=(n_ranks + 1,)).copy()
+        self.ghost_global = (np.ctypeslib.as_array(pv.ghost_global, shape=(self.n_ghost,)).copy()
+                             if self.n_ghost else np.zeros(0, dtype=np.uint64))
+        self.lattice_ids = (np.ctypeslib.as_array(pv.lattice_ids, shape=(self.n_owned + self.n_ghost,)).copy()
+                            if want_lattice_ids else None)
+
+
+class Partitioner:
+    """Utilities::MPI::Partitioner: who sends what to whom.
+
+    ``rank_offsets[r] .. rank_offsets[r+1]`` is rank r's owned global range;
+    ``ghost_global`` are this rank's ghost indices (sorted).  The import side needs the ghost
+    sets of the other ranks: pass ``all_ghosts`` (list per rank) or a process ``group`` to
+    exchange them (the reference runs a consensus algorithm, source/base/partitioner.cc:241-267).
+
+    ghost_targets   [(rank, n)]  ranks owning my ghosts, ascending, with counts
+                    (partitioner.cc:271-300); my ghost section is ordered accordingly
+    import_targets  [(rank, n)]  ranks that ghost my owned dofs
+    import_indices  per import target, the LOCAL owned indices in the order of that rank's
+                    ghost list (compressed to half-open ranges by import_indices_ranges(),
+                    the form tests/mpi/parallel_partitioner_03.cc prints)
+    """
+
+    def __init__(self, rank_offsets, rank, ghost_global, all_ghosts=None, group=None):
+        self.rank = rank
+        self.rank_offsets = np.asarray(rank_offsets, dtype=np.int64)
+        self.n_ranks = len(self.rank_offsets) - 1
+        self.first = int(self.rank_offsets[rank])
+        self.n_owned = int(self.rank_offsets[rank + 1]) - self.first
+        g = np.asarray(ghost_global, dtype=np.int64)
+        assert np.all(np.diff(g) > 0), "ghost indices must be sorted and unique"
+        assert not np.any((g >= self.first) & (g < self.first + self.n_owned)), "ghost index is owned"
+        self.ghost_global = g
+        self.n_ghost = len(g)
+        owner = np.searchsorted(self.rank_offsets, g, side="right") - 1
+        self.ghost_targets = [(int(r), int(c)) for r, c in zip(*np.unique(owner, return_counts=True))]
+        if all_ghosts is None:
+            if self.n_ranks == 1:
+                all_ghosts = [g]
+            else:
+                all_ghosts = [None] * self.n_ranks
+                dist.all_gather_object(all_ghosts, g, group=group)
+        self.import_targets, self.import_indices = [], []
+        for r in range(self.n_ranks):
+            if r == rank:
+                continue
+            gr = np.asarray(all_ghosts[r], dtype=np.int64)
+            mine = gr[(gr >= self.first) & (gr < self.first + self.n_owned)]
+            if len(mine):
+                self.import_targets.append((r, len(mine)))
+                self.import_indices.append((mine - self.first).astype(np.int64))
+        self.n_import = int(sum(c for _, c in self.import_targets))
+
+    def global_to_local(self, gidx):
+        gidx = np.asarray(gidx, dtype=np.int64)
+        own = (gidx >= self.first) & (gidx < self.first + self.n_owned)
+        pos = np.searchsorted(self.ghost_global, gidx)
+        return np.where(own, gidx - self.first, self.n_owned + pos)
+
+    def import_indices_ranges(self):
+        """import_indices_data: half-open local ranges, per target consecutive runs merged."""
+        out = []
+        for idx in self.import_indices:
+            if len(idx) == 0:
+                continue
+            breaks = np.nonzero(np.diff(idx) != 1)[0] + 1
+            starts = np.concatenate(([0], breaks))
+            ends = np.concatenate((breaks, [len(idx)]))
+            out += [(int(idx[s]), int(idx[e - 1]) + 1) for s, e in zip(starts, ends)]
+        return out
+
+    def format_like_reference_test(self):
+        """The text block tests/mpi/parallel_partitioner_03.cc:57-80 writes for this rank."""
+        s = f"**** proc {self.rank}\n"
+        s += "ghost targets: " + "".join(f"[{a}/{b}] " for a, b in self.ghost_targets) + "\n"
+        s += "import targets: " + "".join(f"[{a}/{b}] " for a, b in self.import_targets) + "\n"
+        s += "import indices:\n"
+        s += "".join(f"[{a}/{b})\n" for a, b in self.import_indices_ranges())
+        s += "****\n"
+        return s
+
+
+class GhostExchange:
+    """update_ghost_values / compress(add) of LA::d::Vector over torch.distributed p2p.
+
+    The pack and unpack-add steps are kernels of libb200mf.so; the transport is one grouped
+    batch of isend/irecv (ncclGroupStart .. ncclSend/ncclRecv .. ncclGroupEnd under NCCL)."""
+
+    def __init__(self, partitioner, number, device, group=None):
+        self.part, self.group = partitioner, group
+        self.number_code, self.dtype = (L.F64, torch.float64) if number == "f64" else (L.F32, torch.float32)
+        self.device = torch.device(device)
+        p = partitioner
+        idx = (np.concatenate(p.import_indices) if p.import_indices else np.zeros(0, dtype=np.int64))
+        self.import_idx = torch.from_numpy(idx.astype(np.int32)).to(self.device)
+        self.buf = torch.empty(max(p.n_import, 1), dtype=self.dtype, device=self.device)
+        # slices of the ghost section per owner / of the import buffer per importer
+        self.ghost_slices, off = [], p.n_owned
+        for r, c in p.ghost_targets:
+            self.ghost_slices.append((r, off, off + c))
+            off += c
+        self.import_slices, off = [], 0
+        for r, c in p.import_targets:
+            self.import_slices.append((r, off, off + c))
+            off += c
+        self._lib = L.load() if self.device.type == "cuda" else None
+
+    # -- kernels (CUDA only: the product has no CPU path)
+    def _pack(self, vec):
+        L.check(self._lib.b200mf_ghost_pack(self.number_code, _ptr(self.buf), _ptr(vec), _ptr(self.import_idx),
+                                            self.part.n_import, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def _unpack_add(self, vec):
+        L.check(self._lib.b200mf_ghost_unpack_add(self.number_code, _ptr(vec), _ptr(self.buf), _ptr(self.import_idx),
+                                                  self.part.n_import, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def _transfer(self, vec, to_ghosts):
+        ops = []
+        for r, a, b in self.ghost_slices:          # my ghost section <-> its owner
+            ops.append(dist.P2POp(dist.irecv if to_ghosts else dist.isend, vec[a:b], r, group=self.group))
+        for r, a, b in self.import_slices:         # my packed owned values <-> the rank ghosting them
+            ops.append(dist.P2POp(dist.isend if to_ghosts else dist.irecv, self.buf[a:b], r, group=self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def update_ghost_values_start(self, vec):
+        self._pack(vec)
+        return self._transfer(vec, True)
+
+    def update_ghost_values_finish(self, works):
+        for w in works:
+            w.wait()
+
+    def update_ghost_values(self, vec):
+        self.update_ghost_values_finish(self.update_ghost_values_start(vec))
+
+    def compress_start(self, vec):
+        return self._transfer(vec, False)
+
+    def compress_finish(self, vec, works):
+        for w in works:
+            w.wait()
+        self._unpack_add(vec)
+        self.zero_out_ghost_values(vec)
+
+    def compress(self, vec):
+        self.compress_finish(vec, self.compress_start(vec))
+
+    def zero_out_ghost_values(self, vec):
+        if self.part.n_ghost:
+            vec[self.part.n_owned:].zero_()
+
+
+class DistributedMatrixFree:
+    """Portable::MatrixFree on a partitioned mesh: setup + partitioner + overlapped cell loop."""
+
+    def __init__(self, mesh, number="f64", device="cuda:0", group=None, overlap=True):
+        self.mesh, self.group, self.overlap = mesh, group, overlap
+        self.mf = MatrixFree(number, device).reinit_from_mesh(mesh)
+        self.partitioner = Partitioner(mesh.rank_offsets, mesh.rank, mesh.ghost_global, group=group)
+        self.exchange = GhostExchange(self.partitioner, number, device, group)
+        self.n_owned, self.n_ghost = mesh.n_owned, mesh.n_ghost
+        self.n_cells, self.n_interior = mesh.n_cells, mesh.n_cells_interior
+        self.comm_stream = torch.cuda.Stream(device=self.mf.device)
+        self._lib = L.load()
+
+    def initialize_dof_vector(self):
+        return self.mf.initialize_dof_vector()
+
+    def get_vector_partitioner(self):
+        return self.partitioner
+
+    def _range(self, op, dst, src, a, b, dot):
+        if b <= a:
+            return
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if dot is None:
+            L.check(self._lib.b200mf_cell_loop_range(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b, st))
+        else:
+            L.check(self._lib.b200mf_cell_loop_range_dot(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b,
+                                                         C.c_void_p(dot), st))
+
+    def vmult(self, op, dst, src, dot_ptr=None):
+        """dst = A src on distributed vectors: ghost update || interior cells, cells at the
+        partition boundary, compress || remaining interior cells, copy_constrained_values.
+        dot_ptr: device address of a double accumulating the LOCAL part of src . A src."""
+        main = torch.cuda.current_stream()
+        ex, ni, nc = self.exchange, self.n_interior, self.n_cells
+        single = self.partitioner.n_ranks == 1 or (not ex.ghost_slices and not ex.import_slices)
+        dst.zero_()
+        if single:
+            self._range(op, dst, src, 0, nc, dot_ptr)
+        else:
+            half = ni // 2 if self.overlap else 0
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                works = ex.update_ghost_values_start(src)
+            self._range(op, dst, src, 0, half, dot_ptr)                    # interior, part A
+            with torch.cuda.stream(self.comm_stream):
+                ex.update_ghost_values_finish(works)
+            main.wait_stream(self.comm_stream)
+            self._range(op, dst, src, ni, nc, dot_ptr)                     # cells touching ghosts
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                works = ex.compress_start(dst)
+            self._range(op, dst, src, half, ni, dot_ptr)                   # interior, part B
+            with torch.cuda.stream(self.comm_stream):
+                for w in works:
+                    w.wait()
+            main.wait_stream(self.comm_stream)
+            ex._unpack_add(dst)
+            ex.zero_out_ghost_values(dst)
+            ex.zero_out_ghost_values(src)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if dot_ptr is None:
+            L.check(self._lib.b200mf_copy_constrained_values(self.mf._h, _ptr(dst), _ptr(src), st))
+        else:
+            L.check(self._lib.b200mf_copy_constrained_values_dot(self.mf._h, _ptr(dst), _ptr(src),
+                                                                 C.c_void_p(dot_ptr), st))
+
+    def compute_diagonal(self, op):
+        """MatrixFreeTools::compute_diagonal + compress(add); returns the inverse diagonal."""
+        diag = self.initialize_dof_vector()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(self._lib.b200mf_compute_diagonal(self.mf._h, C.byref(op), _ptr(diag), st))
+        if self.partitioner.n_ranks > 1:
+            self.exchange.compress(diag)
+            L.check(self._lib.b200mf_set_constrained_values(self.mf._h, _ptr(diag), 1.0, st))
+        inv = torch.zeros_like(diag)
+        inv[:self.n_owned] = 1.0 / diag[:self.n_owned]
+        return inv
+
+
+def solve_cg(dmf, op, x, b, inverse_diagonal, tolerance, max_iterations, check_every=1):
+    """SolverCG with Jacobi (or no) preconditioner on distributed vectors; returns
+    (iterations, residual, converged).  Same algebra and stopping rule as b200mf_cg_solve /
+    lac/solver_cg.h:703-763; the three partial sums of an iteration are all-reduced where the
+    reference calls Utilities::MPI::sum."""
+    lib, mf = L.load(), dmf.mf
+    n, code = dmf.n_owned, mf._code
+    dev = mf.device
+    multi = dmf.partitioner.n_ranks > 1
+    r, p, v = (dmf.initialize_dof_vector() for _ in range(3))
+    sc = torch.zeros(24, dtype=torch.float64, device=dev)
+    base = sc.data_ptr()
+    d = _ptr(inverse_diagonal) if inverse_diagonal is not None else None
+
+    def stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def slot(k):
+        return 8 * (k % 3)
+
+    def allreduce(view):
+        if multi:
+            dist.all_reduce(view, group=dmf.group)
+
+    h = (C.c_double * 1)()
+    L.check(lib.b200mf_vec_dot(code, _ptr(x), _ptr(x), n, h, stream()))
+    xx = torch.tensor([h[0]], dtype=torch.float64, device=dev)
+    allreduce(xx)
+    x_zero = float(xx) == 0.0
+    if not x_zero:
+        dmf.vmult(op, v, x)
+    L.check(lib.b200mf_cg_init(code, _ptr(r), _ptr(p), _ptr(b), None if x_zero else _ptr(v), d, n,
+                               C.c_void_p(base), stream()))
+    allreduce(sc[slot(1) + 1:slot(1) + 3])
+    res = float(sc[slot(1) + 1]) ** 0.5
+    it = 0
+    if res <= tolerance:
+        return 0, res, True
+    while True:
+        it += 1
+        s0, s1 = slot(it), slot(it + 1)
+        dmf.vmult(op, v, p, dot_ptr=base + 8 * s0)
+        allreduce(sc[s0:s0 + 1])
+        L.check(lib.b200mf_cg_post(code, _ptr(r), _ptr(v), d, n, C.c_void_p(base), it, stream()))
+        allreduce(sc[s1 + 1:s1 + 3])
+        done = False
+        if it % check_every == 0 or it >= max_iterations:
+            res = float(sc[s1 + 1]) ** 0.5
+            done = res <= tolerance or it >= max_iterations or res != res
+        if done:
+            L.check(lib.b200mf_cg_final(code, _ptr(x), _ptr(p), n, C.c_void_p(base), it, stream()))
+            return it, res, res <= tolerance
+        L.check(lib.b200mf_cg_pre(code, _ptr(x), _ptr(p), _ptr(r), d, n, C.c_void_p(base), it, stream()))

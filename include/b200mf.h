@@ -149,6 +149,11 @@ typedef struct {
  * (portable_matrix_free.h:562; serial_cell_loop portable_matrix_free.templates.h:1440). */
 int b200mf_cell_loop(const b200mf_setup *s, const b200mf_operator *op, void *dst,
                      const void *src, void *stream);
+/* The same over the local cells [cell_begin, cell_end): the pieces distributed_cell_loop
+ * interleaves with the ghost exchange (portable_matrix_free.templates.h:1602-1656).      */
+int b200mf_cell_loop_range(const b200mf_setup *s, const b200mf_operator *op, void *dst,
+                           const void *src, uint64_t cell_begin, uint64_t cell_end,
+                           void *stream);
 /* Operator::vmult of the reference's users: dst = 0; cell_loop; copy_constrained_values
  * (examples/step-64/step-64.cc:313-325; MatrixFreeOperators::Base::vmult
  * matrix_free/operators.h:1487 for setups built with B200MF_L2G_CONSTRAINED bits).      */
@@ -214,6 +219,41 @@ typedef struct {
 int b200mf_cg_solve(const b200mf_setup *s, const b200mf_operator *op,
                     const b200mf_solver_desc *solver, void *x, const void *b,
                     b200mf_solver_result *result, void *stream);
+/* Building blocks of the same fused CG for callers that interleave their own communication
+ * (multi-GPU: all-reduce of the scalar slots between the kernels, see dealii_b200/distributed.py
+ * and INTEGRATION.md).  `scratch`: caller-owned, zero-initialised device array of 24 doubles,
+ * slot(k) = scratch + 8*(k%3) = [p.Ap, r.r, r.z] of iteration k
+ * (the partial sums of lac/solver_cg.h:871-893).
+ *   init : r = b - Ax (Ax may be NULL), p = D^-1 r;   slot(1)[1,2] += r.r, r.z
+ *   post : alpha = slot(it)[2]/slot(it)[0]; r -= alpha v;  slot(it+1)[1,2] += r.r, r.D^-1 r
+ *   pre  : x += alpha p; p = beta p + D^-1 r (beta = slot(it+1)[2]/slot(it)[2]); slot(it+2) = 0
+ *   final: x += alpha p
+ * d = NULL => PreconditionIdentity.                                                      */
+int b200mf_cg_init(int number, void *r, void *p, const void *b, const void *Ax, const void *d,
+                   uint64_t n, double *scratch, void *stream);
+int b200mf_cg_post(int number, void *r, const void *v, const void *d, uint64_t n, double *scratch,
+                   int it, void *stream);
+int b200mf_cg_pre(int number, void *x, void *p, const void *r, const void *d, uint64_t n,
+                  double *scratch, int it, void *stream);
+int b200mf_cg_final(int number, void *x, const void *p, uint64_t n, const double *scratch, int it,
+                    void *stream);
+/* cell loop over a cell range that also accumulates src.(A src) of these cells into the
+ * device double *dot_accum (the p.Ap of CG); copy_constrained_values adding src_c^2.      */
+int b200mf_cell_loop_range_dot(const b200mf_setup *s, const b200mf_operator *op, void *dst,
+                               const void *src, uint64_t cell_begin, uint64_t cell_end,
+                               double *dot_accum, void *stream);
+int b200mf_copy_constrained_values_dot(const b200mf_setup *s, void *dst, const void *src,
+                                       double *dot_accum, void *stream);
+
+/* Ghost exchange kernels: Utilities::MPI::Partitioner::export_to_ghosted_array_start packs
+ * buf[i] = vec[import_indices[i]] (base/partitioner.templates.h:119-137);
+ * import_from_ghosted_array_finish adds vec[import_indices[i]] += buf[i] (:604-671).
+ * The transport between ranks (ncclSend/ncclRecv) is the caller's.                        */
+int b200mf_ghost_pack(int number, void *buf, const void *vec, const uint32_t *import_indices,
+                      uint64_t n, void *stream);
+int b200mf_ghost_unpack_add(int number, void *vec, const void *buf,
+                            const uint32_t *import_indices, uint64_t n, void *stream);
+
 /* x and b are HOST arrays of n_owned_dofs elements (copies inside).                      */
 int b200mf_cg_solve_host(const b200mf_setup *s, const b200mf_operator *op,
                          const b200mf_solver_desc *solver, void *x_host, const void *b_host,
@@ -248,6 +288,41 @@ typedef struct {
 } b200mf_mesh_view;
 
 int b200mf_mesh_create(const b200mf_mesh_desc *desc, b200mf_mesh **out);
+
+/* The same mesh partitioned like parallel::distributed::Triangulation (p4est): the active
+ * cells in Morton order are cut into n_ranks equal contiguous chunks; DoFs on partition
+ * interfaces belong to the lowest rank touching them and every rank numbers its owned DoFs
+ * by first touch over its own cells, shifted by the DoF counts of the lower ranks
+ * (source/dofs/dof_handler_policy.cc:3644-3760).  The domain is coarse[0] x coarse[1] x
+ * coarse[2] unit cubes (subdivided_hyper_rectangle, lexicographic) each refined
+ * log2(cells_per_direction) times; the chunks must be boxes (n_ranks = number of coarse cells,
+ * or one coarse cell and n_ranks a power of two).  Every rank builds ITS part only, with no
+ * communication; local indices follow LinearAlgebra::distributed::Vector /
+ * Utilities::MPI::Partitioner: [owned | ghosts sorted by global index].                 */
+enum { B200MF_GHOSTS_RELEVANT = 0, /* all dofs of ghost cells: Portable::MatrixFree's set
+                                      (portable_matrix_free.templates.h:1326-1343)         */
+       B200MF_GHOSTS_TOUCHED = 1   /* only dofs the own cells touch: CPU MatrixFree's tight
+                                      set (source/matrix_free/dof_info.cc:145-262)         */ };
+typedef struct {
+  b200mf_mesh_desc mesh; /* cell_order must be B200MF_MESH_MORTON                          */
+  int coarse[3];         /* coarse cells per direction (0 => 1)                            */
+  int n_ranks, rank;
+  int ghost_mode;        /* B200MF_GHOSTS_*                                                */
+  int want_lattice_ids;  /* 1 => also return the global lattice id of every local dof (tests) */
+} b200mf_partition_desc;
+
+typedef struct {
+  uint64_t n_global_dofs, n_global_cells;
+  uint64_t first_owned_global; /* start of this rank's contiguous global range            */
+  uint64_t n_owned, n_ghost;
+  uint64_t n_cells_interior;   /* local cells [0, n_cells_interior) touch no ghost dof      */
+  const uint64_t *rank_offsets;  /* [n_ranks + 1] global range starts of all ranks          */
+  const uint64_t *ghost_global;  /* [n_ghost] sorted global indices of the ghost dofs        */
+  const uint64_t *lattice_ids;   /* [n_owned + n_ghost] or NULL                             */
+} b200mf_partition_view;
+
+int b200mf_mesh_create_partitioned(const b200mf_partition_desc *desc, b200mf_mesh **out);
+int b200mf_mesh_partition_view_get(const b200mf_mesh *m, b200mf_partition_view *view);
 int b200mf_mesh_view_get(const b200mf_mesh *m, b200mf_mesh_view *view);
 int b200mf_mesh_destroy(b200mf_mesh *m);
 /* Convenience: setup straight from a generated mesh. */

@@ -1,0 +1,107 @@
+"""Distributed operator / CG on the GPU(s): DistributedMatrixFree + NCCL ghost exchange against
+the serial oracle (vmult per entry through lattice ids) and against the single-rank solver
+(iteration counts).  The multi-rank cases need >= 2 GPUs and are skipped otherwise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import dealii_b200
+from dealii_b200.distributed import DistributedMatrixFree, PartitionedHyperCubeMesh, solve_cg
+from oracle.mesh import HyperCubeMesh as OracleMesh
+from oracle.mf_oracle import MatrixFreeOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _value(lat):
+    return np.sin(0.37 * lat.astype(np.float64)) + 1.5
+
+
+def _run_rank(rank, world, port, dim, degree, refinements, amp, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        pm = PartitionedHyperCubeMesh(dim, degree, refinements, world, rank, want_lattice_ids=True,
+                                      dirichlet_boundary=True, deformation_amplitude=amp)
+        dmf = DistributedMatrixFree(pm, "f64", dev)
+        A = dealii_b200.LaplaceOperator(dmf.mf)
+        src = dmf.initialize_dof_vector()
+        src[:pm.n_owned] = torch.from_numpy(_value(pm.lattice_ids[:pm.n_owned])).to(dev)
+        dmf.mf.set_constrained_values(0.0, src)
+        dst = dmf.initialize_dof_vector()
+        dmf.vmult(A.op, dst, src)
+        torch.cuda.synchronize()
+        ghost_clean = float(src[pm.n_owned:].abs().max()) if pm.n_ghost else 0.0
+        # CG + Jacobi, rhs = 1 on unconstrained dofs
+        inv = dmf.compute_diagonal(A.op)
+        b = dmf.initialize_dof_vector()
+        b[:pm.n_owned] = 1.0
+        dmf.mf.set_constrained_values(0.0, b)
+        x = dmf.initialize_dof_vector()
+        bn = torch.tensor([float(torch.dot(b[:pm.n_owned], b[:pm.n_owned]))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bn)
+        its, res, ok = solve_cg(dmf, A.op, x, b, inv, 1e-10 * float(bn) ** 0.5, 2000)
+        ret[rank] = (pm.lattice_ids[:pm.n_owned].copy(), dst[:pm.n_owned].cpu().numpy(), ghost_clean,
+                     its, ok, x[:pm.n_owned].cpu().numpy(), inv[:pm.n_owned].cpu().numpy())
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _reference(dim, degree, refinements, amp):
+    defo = (lambda v: v + amp * np.prod(np.sin(np.pi * v), axis=1, keepdims=True)) if amp else None
+    om = OracleMesh(dim, degree, refinements=refinements, deformation=defo)
+    o = MatrixFreeOracle(om, constrained_dofs=om.boundary_dofs)
+    lat_points = np.nonzero(om._number_of_lattice >= 0)[0]
+    src = np.zeros(om.n_dofs)
+    src[om._number_of_lattice[lat_points]] = _value(lat_points)
+    src[om.boundary_dofs] = 0.0
+    return om, o, o.vmult(src)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("dim,degree,refinements,amp", [(3, 4, 2, 0.0), (3, 2, 3, 0.05), (2, 3, 4, 0.0)])
+def test_distributed_vmult_and_cg(world, dim, degree, refinements, amp):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29600 + (os.getpid() % 2000)
+    if world == 1:
+        ret = {}
+        _run_rank(0, 1, port, dim, degree, refinements, amp, ret)
+    else:
+        ret = mp.Manager().dict()
+        mp.spawn(_run_rank, args=(world, port, dim, degree, refinements, amp, ret), nprocs=world, join=True)
+    om, o, ref = _reference(dim, degree, refinements, amp)
+    ref_diag = o.compute_diagonal()
+    its = set()
+    for rank in range(world):
+        lat, dst, ghost_clean, it, ok, x, inv = ret[rank]
+        ser = om._number_of_lattice[lat]
+        assert np.abs(dst - ref[ser]).max() <= 1e-12 * np.abs(ref).max()
+        assert np.abs(inv * ref_diag[ser] - 1.0).max() < 1e-12
+        assert ghost_clean == 0.0 and ok
+        its.add(it)
+    assert len(its) == 1
+    # iteration count of the single-rank engine solver on the same problem (+-1)
+    mf = dealii_b200.MatrixFree("f64").reinit(dim, degree, om.l2g.astype(np.uint32), cell_vertices=om.cell_vertices,
+                                              constrained_dofs=om.boundary_dofs, n_owned_dofs=om.n_dofs)
+    A = dealii_b200.LaplaceOperator(mf)
+    invd = A.compute_diagonal()
+    b = torch.ones(om.n_dofs, dtype=torch.float64, device="cuda")
+    mf.set_constrained_values(0.0, b)
+    x = mf.initialize_dof_vector()
+    control = dealii_b200.SolverControl(2000, 1e-10 * float(b.norm()))
+    dealii_b200.SolverCG(control).solve(A, x, b, invd)
+    assert abs(control.last_step() - its.pop()) <= 1
+    xs = x.cpu().numpy()
+    for rank in range(world):
+        lat, _, _, _, _, xr, _ = ret[rank]
+        assert np.abs(xr - xs[om._number_of_lattice[lat]]).max() < 1e-8 * np.abs(xs).max()

@@ -1,0 +1,161 @@
+"""Partitioned mesh generator and Partitioner index algebra (host logic, no GPU).
+
+* the product's Partitioner reproduces tests/mpi/parallel_partitioner_03.mpirun=4.output;
+* the product's partitioned mesh generator reproduces the oracle's restatement of
+  parallel::distributed numbering bit-exactly (global numbers, owned ranges, ghost sets);
+* a world_size-2 gloo run exchanges ghost values / compresses on CPU and reproduces the serial
+  oracle's vmult with the oracle cell operator applied to each rank's local cells."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import dealii_b200
+from dealii_b200.distributed import GhostExchange, PartitionedHyperCubeMesh, Partitioner
+from oracle.mesh import HyperCubeMesh as OracleMesh
+from oracle.mf_oracle import MatrixFreeOracle
+from oracle.partition import distributed_numbering, relevant_dofs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_partitioner_matches_reference_golden():
+    nproc, s = 4, 200
+    offsets, start = [0], 0
+    for r in range(nproc):
+        start += s - r
+        offsets.append(start)
+    ghosts = np.array([1, 2, 13, s - 2, s - 1, s, s + 1, 2 * s, 2 * s + 1, 2 * s + 3])
+    per_rank = []
+    for r in range(nproc):
+        g = ghosts[(ghosts < offsets[r]) | (ghosts >= offsets[r + 1])]
+        per_rank.append(np.unique(g))
+    text = "".join(Partitioner(offsets, r, per_rank[r], all_ghosts=per_rank).format_like_reference_test()
+                   for r in range(nproc))
+    golden = open(os.path.join(GOLD, "parallel_partitioner_03.mpirun=4.output")).read()
+    golden = golden[golden.index("**** proc 0"):]
+    assert text.split() == golden.split()
+
+
+@pytest.mark.parametrize("dim,degree,refinements,n_ranks", [
+    (3, 2, 2, 2), (3, 2, 2, 4), (3, 3, 2, 8), (3, 1, 3, 8), (2, 3, 3, 4), (2, 2, 3, 2), (3, 4, 1, 8),
+    (3, 2, 2, 1)])
+@pytest.mark.parametrize("mode", ["relevant", "touched"])
+def test_partitioned_numbering_matches_oracle(dim, degree, refinements, n_ranks, mode):
+    om = OracleMesh(dim, degree, refinements=refinements)
+    num = distributed_numbering(om, n_ranks)
+    L = om.lattice_size
+    serial_of_lat = om._number_of_lattice
+    lat_points = np.nonzero(serial_of_lat >= 0)[0]
+    lat_of_serial = np.zeros(om.n_dofs, dtype=np.int64)
+    lat_of_serial[serial_of_lat[lat_points]] = lat_points
+    seen = np.zeros(om.n_dofs, dtype=int)
+    for rank in range(n_ranks):
+        pm = PartitionedHyperCubeMesh(dim, degree, refinements, n_ranks, rank, ghost_mode=mode,
+                                      want_lattice_ids=True, dirichlet_boundary=True)
+        assert np.array_equal(pm.rank_offsets, num["rank_offsets"])
+        assert pm.n_global_dofs == om.n_dofs
+        # global number of every local dof through its lattice id
+        serial = serial_of_lat[pm.lattice_ids]
+        glob_expected = num["global_of_serial"][serial]
+        glob_local = np.concatenate((pm.first_owned_global + np.arange(pm.n_owned), pm.ghost_global)).astype(np.int64)
+        assert np.array_equal(glob_local, glob_expected)
+        seen[serial[:pm.n_owned]] += 1
+        # ghost set
+        assert np.array_equal(pm.ghost_global.astype(np.int64), relevant_dofs(om, num, rank, mode))
+        # index lists: same cells (as sets of lattice points), interior cells touch no ghost
+        own_cells = np.nonzero(num["cell_rank"] == rank)[0]
+        expect = np.sort(lat_of_serial[om.l2g[own_cells]], axis=1)
+        got = np.sort(pm.lattice_ids[pm.l2g & 0x7FFFFFFF].astype(np.int64), axis=1)
+        assert sorted(map(tuple, got)) == sorted(map(tuple, expect))
+        assert (pm.l2g[:pm.n_cells_interior] < pm.n_owned).all()
+        if pm.n_cells_interior < pm.n_cells and mode == "touched":
+            assert (pm.l2g[pm.n_cells_interior:] >= pm.n_owned).any(axis=1).all()
+        # lexicographic order inside a cell is preserved: x fastest lattice ids
+        lat = pm.lattice_ids[pm.l2g[0]]
+        assert np.array_equal(np.sort(lat), lat) or dim > 1
+        # Dirichlet list = owned boundary dofs
+        coords = np.stack([(pm.lattice_ids[:pm.n_owned] // L ** d) % L for d in range(dim)], 1)
+        bnd = np.nonzero(((coords == 0) | (coords == L - 1)).any(axis=1))[0]
+        assert np.array_equal(pm.boundary_dofs, bnd)
+    assert (seen == 1).all()
+
+
+def test_single_rank_partition_equals_serial_generator():
+    a = dealii_b200.HyperCubeMesh(3, 3, refinements=2)
+    b = PartitionedHyperCubeMesh(3, 3, 2, 1, 0)
+    assert np.array_equal(a.l2g, b.l2g) and b.n_ghost == 0 and b.n_cells_interior == b.n_cells
+
+
+def test_coarse_grid_partition_one_cube_per_rank():
+    # subdivided_hyper_rectangle(1,1,2) refined once, two ranks: each owns one cube
+    tot = 0
+    for rank in range(2):
+        pm = PartitionedHyperCubeMesh(3, 2, 1, 2, rank, coarse=(1, 1, 2), want_lattice_ids=True)
+        tot += pm.n_owned
+        assert pm.n_cells == 8
+    assert tot == 5 * 5 * 9 and pm.n_global_dofs == tot
+
+
+# ----------------------------------------------------------------------------------------------
+class _CpuExchange(GhostExchange):
+    """Test-only plumbing: pack / unpack-add with torch CPU ops so the host-side message plan
+    can run under gloo without a GPU (the product's kernels are CUDA only)."""
+
+    def _pack(self, vec):
+        self.buf[:self.part.n_import] = vec[self.import_idx.long()]
+
+    def _unpack_add(self, vec):
+        vec.index_add_(0, self.import_idx.long(), self.buf[:self.part.n_import])
+
+
+def _worker(rank, world, port, dim, degree, refinements, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pm = PartitionedHyperCubeMesh(dim, degree, refinements, world, rank, want_lattice_ids=True)
+        part = Partitioner(pm.rank_offsets, rank, pm.ghost_global)        # all_gather_object over gloo
+        ex = _CpuExchange(part, "f64", "cpu")
+        # src = f(lattice id): identical global vector on every partition
+        val = lambda lat: np.sin(0.37 * lat.astype(np.float64)) + 1.5
+        vec = torch.zeros(pm.n_owned + pm.n_ghost, dtype=torch.float64)
+        vec[:pm.n_owned] = torch.from_numpy(val(pm.lattice_ids[:pm.n_owned]))
+        ex.update_ghost_values(vec)
+        ok_ghost = np.allclose(vec.numpy(), val(pm.lattice_ids))
+        # local cell operator with the oracle on this rank's cells, then compress(add)
+        class _M:  # minimal mesh view for the oracle
+            pass
+        m = _M()
+        m.dim, m.degree, m.n_cells, m.n_dofs = dim, degree, pm.n_cells, pm.n_owned + pm.n_ghost
+        m.l2g, m.cell_vertices = pm.l2g.astype(np.int64), pm.cell_vertices
+        loc = MatrixFreeOracle(m).cell_loop(vec.numpy())
+        dst = torch.from_numpy(loc.copy())
+        ex.compress(dst)
+        ret[rank] = (ok_ghost, pm.lattice_ids[:pm.n_owned].copy(), dst[:pm.n_owned].numpy().copy(),
+                     float(dst[pm.n_owned:].abs().max()) if pm.n_ghost else 0.0)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dim,degree,refinements", [(3, 2, 2), (2, 3, 3)])
+def test_gloo_two_ranks_ghost_exchange_and_vmult(dim, degree, refinements):
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, dim, degree, refinements, ret), nprocs=world, join=True)
+    om = OracleMesh(dim, degree, refinements=refinements)
+    lat_all = np.nonzero(om._number_of_lattice >= 0)[0]
+    src = np.zeros(om.n_dofs)
+    src[om._number_of_lattice[lat_all]] = np.sin(0.37 * lat_all.astype(np.float64)) + 1.5
+    ref = MatrixFreeOracle(om).cell_loop(src)
+    covered = 0
+    for rank in range(world):
+        ok_ghost, lat, dst, ghost_max = ret[rank]
+        assert ok_ghost and ghost_max == 0.0
+        expect = ref[om._number_of_lattice[lat]]
+        assert np.abs(dst - expect).max() <= 1e-12 * np.abs(ref).max()
+        covered += len(lat)
+    assert covered == om.n_dofs
