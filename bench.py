@@ -6,8 +6,10 @@
 
 Workload (BASELINE.json configs[1]): 3D Q4 Laplace vmult, FP64, affine Cartesian hyper_cube
 refined globally 7 times (128^3 cells, 513^3 = 135,005,697 DoFs) per GPU; a "step" is one
-vmult (dst = 0; cell loop; copy_constrained_values) over the whole mesh.  At N > 1 every rank
-owns its own sub-cube of that size (weak scaling, one process per GPU).
+vmult (dst = 0; cell loop; copy_constrained_values) over the whole mesh.  At N > 1 the domain is
+N such cubes (subdivided_hyper_rectangle, one cube per rank, p4est-style partition and DoF
+numbering), vectors are [owned | ghosts], and every vmult does update_ghost_values (NCCL
+send/recv over NVLink, overlapped with the interior cells) and compress(add): weak scaling.
 
 One JSON line on stdout (rank 0), see the task contract: value = whole-job GDoF/s with the
 vectors resident in HBM, e2e = the same through the C-ABI host entry point
@@ -38,7 +40,7 @@ CG_BYTES_PER_DOF = {"f64": 72.0, "f32": 36.0}        # fused Jac
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--degree", type=int, default=4)
@@ -47,9 +49,24 @@ def parse_args():
     ap.add_argument("--deformation", type=float, default=0.0)
     ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ghosts", default="relevant", choices=["relevant", "touched"],
+                    help="ghost set: Portable::MatrixFree's locally relevant dofs or the tight touched set")
     ap.add_argument("--cpu-refinements", type=int, default=6,
                     help="per-core sub-cube of the CPU baseline sample")
     return ap.parse_args()
+
+
+def kernel_name(args):
+    """The kernel the dispatch policy of csrc/cell_inst.cu picks for this workload."""
+    n, f64, general = args.degree + 1, args.number == "f64", args.deformation != 0.0
+    plane = (n <= 4 if f64 else (n <= 3 or n == 5)) if general else n <= 5
+    if os.environ.get("B200MF_KERNEL") == "v1":
+        plane = False
+    if os.environ.get("B200MF_KERNEL") == "plane" and n <= 6:
+        plane = True
+    t = "double" if f64 else "float"
+    kind = "GENERAL" if general else "CARTESIAN"
+    return (f"cell_loop_plane_kernel<{n},{t},{kind}>" if plane else f"cell_loop_kernel<3,{n},{t},{kind}>")
 
 
 def measured_peak():
@@ -200,22 +217,29 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- setup: every rank owns one hyper_cube(refinements) sub-domain
-    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements,
-                                     deformation_amplitude=args.deformation)
-    mf = dealii_b200.MatrixFree(args.number, dev).reinit_from_mesh(mesh)
+    # ---- setup: one cube of the workload per rank, partitioned like p4est
+    from dealii_b200.distributed import DistributedMatrixFree, PartitionedHyperCubeMesh, solve_cg
+    coarse = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
+    assert coarse is not None, "bench.py supports 1, 2, 4 or 8 GPUs"
+    mesh = PartitionedHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
+                                    deformation_amplitude=args.deformation, ghost_mode=args.ghosts)
+    dmf = DistributedMatrixFree(mesh, args.number, dev)
+    mf = dmf.mf
     op = dealii_b200.LaplaceOperator(mf)
-    n_dofs = mf.n_owned
-    n_total = n_dofs * world
+    n_dofs = mesh.n_owned
+    n_total = mesh.n_global_dofs
     tdt = mf.torch_dtype
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
-    src = torch.rand(n_dofs, dtype=tdt, device=dev, generator=gen)
-    dst = mf.initialize_dof_vector()
-    launches0 = lib.b200mf_kernel_launch_count()
+    src = dmf.initialize_dof_vector()
+    src[:n_dofs] = torch.rand(n_dofs, dtype=tdt, device=dev, generator=gen)
+    dst = dmf.initialize_dof_vector()
+
+    def step():
+        dmf.vmult(op.op, dst, src)
 
     # ---- value: K vmults, vectors resident in HBM
     for _ in range(max(args.warmup, 3)):
-        op.vmult(dst, src)
+        step()
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -224,7 +248,7 @@ def run_engine(args):
     lc0 = lib.b200mf_kernel_launch_count()
     e0.record()
     for _ in range(args.steps):
-        op.vmult(dst, src)
+        step()
     e1.record()
     torch.cuda.synchronize()
     lc1 = lib.b200mf_kernel_launch_count()
@@ -255,35 +279,51 @@ def run_engine(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                "kernel": "cell_loop_kernel<3,%d,%s>" % (args.degree + 1,
-                                                         "double" if args.number == "f64" else "float"),
+                "kernel": kernel_name(args),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_dof": bpd, "peak_source": peak_src,
                 "note": ("FP64 sum factorisation is co-bound by the FP64 pipe (37.1 TFLOP/s measured, "
                          "tools/fp64_peak.cu); see DESIGN.md")}
 
-    # ---- e2e: the C-ABI host entry point, host<->device copies inside the timed region
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region.  N = 1: the
+    # C-ABI host entry point b200mf_vmult_host; N > 1: the public distributed vmult between a
+    # pinned-host H2D of the owned part and a D2H of the result (ghost exchange included).
     nbytes = n_dofs * (8 if args.number == "f64" else 4)
     h_src = torch.empty(n_dofs, dtype=tdt).pin_memory()
     h_dst = torch.empty(n_dofs, dtype=tdt).pin_memory()
-    h_src.copy_(src)
+    h_src.copy_(src[:n_dofs])
+
+    def e2e_step():
+        if world == 1:
+            op.vmult_host(h_dst.numpy(), h_src.numpy())
+        else:
+            src[:n_dofs].copy_(h_src, non_blocking=True)
+            step()
+            h_dst.copy_(dst[:n_dofs], non_blocking=True)
+            torch.cuda.synchronize()
+
     e2e_steps = max(2, min(args.steps, 5))
-    op.vmult_host(h_dst.numpy(), h_src.numpy())
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        op.vmult_host(h_dst.numpy(), h_src.numpy())
+        e2e_step()
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": n_total * e2e_steps / t_e2e / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
-           "api": "b200mf_vmult_host (include/b200mf.h)"}
-    check = float((h_dst[:1000].to(dev) - dst[:1000]).abs().max())  # same result as device path
+           "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": e2e_steps,
+           "api": ("b200mf_vmult_host (include/b200mf.h)" if world == 1 else
+                   "DistributedMatrixFree.vmult between pinned-host H2D and D2H copies")}
+    step()
+    torch.cuda.synchronize()
+    # atomics make the summation order (hence the last bits) run-dependent: compare to 1e-12
+    check = float((h_dst[:100000].to(dev) - dst[:100000]).abs().max() / dst[:100000].abs().max())
     del h_src, h_dst
 
     # ---- CG + Jacobi (the second half of the metric): DoF-iterations/s
     cg = None
     if not args.no_cg:
-        cg = run_cg(args, dev, rank, world, barrier, max_over_ranks, peak)
+        del dst, src
+        cg = run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak)
 
     launches = lc1 - lc0
     cpu = None
@@ -299,52 +339,50 @@ def run_engine(args):
                 "dtype": args.number, "data": "synthetic",
                 "config": workload_config(args, n_total,
                                           "1 GPU" if world == 1 else
-                                          f"{world} ranks, one sub-cube per GPU"),
+                                          f"{world} ranks (1 per GPU), domain decomposition, {args.ghosts} "
+                                          f"ghosts: {mesh.n_ghost} per rank, NCCL p2p exchange"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "cg": cg,
-                "e2e_matches_device": check == 0.0}
+                "e2e_matches_device": bool(check < 1e-12)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_cg(args, dev, rank, world, barrier, max_over_ranks, peak):
-    """SolverCG + Jacobi on the same mesh with zero Dirichlet boundary, rhs = 1: a fixed
-    number of iterations (the solve is stopped by max_iterations, like IterationNumberControl)."""
+def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
+    """SolverCG + Jacobi on the same (partitioned) mesh with zero Dirichlet boundary, rhs = 1:
+    a fixed number of iterations (stopped by max_iterations, like IterationNumberControl)."""
     import torch
     import dealii_b200
-    from dealii_b200 import _lib as L
-    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements,
-                                     deformation_amplitude=args.deformation, dirichlet_boundary=True)
-    mf = dealii_b200.MatrixFree(args.number, dev).reinit_from_mesh(mesh)
-    A = dealii_b200.LaplaceOperator(mf)
-    inv_diag = A.compute_diagonal()
-    b = torch.ones(mf.n_owned, dtype=mf.torch_dtype, device=dev)
-    mf.set_constrained_values(0.0, b)
-    iters = max(args.steps, 10)
-    best = None
+    from dealii_b200.distributed import DistributedMatrixFree, PartitionedHyperCubeMesh, solve_cg
+    mesh = PartitionedHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
+                                    deformation_amplitude=args.deformation, dirichlet_boundary=True,
+                                    ghost_mode=args.ghosts)
+    dmf = DistributedMatrixFree(mesh, args.number, dev)
+    A = dealii_b200.LaplaceOperator(dmf.mf)
+    inv_diag = dmf.compute_diagonal(A.op)
+    b = dmf.initialize_dof_vector()
+    b[:mesh.n_owned] = 1.0
+    dmf.mf.set_constrained_values(0.0, b)
+    iters = max(min(args.steps, 30), 10)
+    best, its, res = None, 0, 0.0
     for rep in range(2):                      # first solve = warm-up
-        x = mf.initialize_dof_vector()
-        control = dealii_b200.SolverControl(iters, 1e-300)
+        x = dmf.initialize_dof_vector()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        try:
-            dealii_b200.SolverCG(control).solve(A, x, b, inv_diag)
-        except L.B200MFError as err:          # NoConvergence by construction
-            if err.code != L.ERR_NOCONVERGENCE:
-                raise
+        its, res, _ = solve_cg(dmf, A.op, x, b, inv_diag, 1e-300, iters)
         e1.record()
         torch.cuda.synchronize()
         best = max_over_ranks(e0.elapsed_time(e1))
-    its = control.last_step()
-    n_total = mf.n_owned * world
+    n_total = mesh.n_global_dofs
     val = n_total * its / (best * 1e-3) / 1e9
     bpd = CG_BYTES_PER_DOF[args.number]
     return {"metric": "cg_jacobi_throughput", "value": val, "unit": "GDoF-iterations/s",
-            "iterations": its, "ms_per_iteration": best / max(its, 1), "residual": control.last_value(),
-            "roofline_frac": bpd * mf.n_owned * its / (best * 1e-3) / 1e9 / peak,
-            "algorithmic_bytes_per_dof_iteration": bpd}
+            "iterations": its, "ms_per_iteration": best / max(its, 1), "residual": res,
+            "roofline_frac": bpd * n_total / world * its / (best * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_dof_iteration": bpd,
+            "api": "dealii_b200.distributed.solve_cg (b200mf_cg_* kernels + all-reduce of the CG scalars)"}
 
 
 if __name__ == "__main__":

@@ -35,7 +35,8 @@ def test_struct_layout_matches_header_sizes(tmp_path):
     structs = {"b200mf_setup_desc": L.SetupDesc, "b200mf_setup_info": L.SetupInfo,
                "b200mf_operator": L.Operator, "b200mf_solver_desc": L.SolverDesc,
                "b200mf_solver_result": L.SolverResult, "b200mf_mesh_desc": L.MeshDesc,
-               "b200mf_mesh_view": L.MeshView}
+               "b200mf_mesh_view": L.MeshView, "b200mf_partition_desc": L.PartitionDesc,
+               "b200mf_partition_view": L.PartitionView}
     src = tmp_path / "sizes.c"
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text('#include <stdio.h>\n#include "b200mf.h"\nint main(void){' + body + 'return 0;}\n')
@@ -57,3 +58,28 @@ def test_no_cpu_fallback():
     h = C.c_void_p()
     rc = L.load().b200mf_setup_create_from_mesh(m._h, L.F64, C.byref(h))
     assert rc == L.ERR_CUDA and b"no CPU fallback" in L.load().b200mf_last_error()
+
+
+def _build_cxx_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "step64_like"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "examples", "step64_like.cc"), "-L", os.path.join(ROOT, "dealii_b200"),
+                           "-lb200mf", "-L/usr/local/cuda/lib64", "-lcudart", "-o", str(exe)])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "dealii_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return subprocess.run([str(exe)], env=env, capture_output=True, text=True)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_cxx_shim_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """include/b200mf_portable.hpp (the Portable::MatrixFree-shaped C++ shim) builds against
+    the C ABI with plain g++; without a device the program dies on b200::Exception."""
+    r = _build_cxx_example(tmp_path)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cxx_shim_step64_like_runs(tmp_path):
+    r = _build_cxx_example(tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "Solved in" in r.stdout and "15625 DoFs" in r.stdout
