@@ -37,7 +37,8 @@ class SetupInfo(C.Structure):
     _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("n_q_points_1d", C.c_int), ("number", C.c_int),
                 ("n_cells", u64), ("n_owned_dofs", u64), ("n_ghost_dofs", u64), ("n_constrained_dofs", u64),
                 ("cell_kind", C.c_int), ("n_distinct_geometries", u64), ("device_bytes", u64),
-                ("geometry_bytes", u64), ("index_bytes", u64)]
+                ("geometry_bytes", u64), ("index_bytes", u64),
+                ("n_bricks", u64), ("cells_per_brick", u64)]
 
 
 class Operator(C.Structure):

@@ -2,6 +2,7 @@
 // (cell_loop / vmult / copy_constrained_values / compute_diagonal).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <unordered_map>
@@ -30,6 +31,27 @@ size_t number_size(int number) { return number == B200MF_F64 ? 8 : 4; }
                         uint64_t, cudaStream_t, bool, double *);
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
+#define DECL_N(N)                                                                              \
+  int launch_bricks_n##N(const Setup &, const b200mf_operator &, void *, const void *, uint64_t, \
+                         uint64_t, cudaStream_t, double *, bool);
+DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
+#undef DECL_N
+
+int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                  uint64_t bb, uint64_t nb, cudaStream_t st, double *dot, bool ow) {
+  switch (s.n) {
+    case 2: return launch_bricks_n2(s, op, dst, src, bb, nb, st, dot, ow);
+    case 3: return launch_bricks_n3(s, op, dst, src, bb, nb, st, dot, ow);
+    case 4: return launch_bricks_n4(s, op, dst, src, bb, nb, st, dot, ow);
+    case 5: return launch_bricks_n5(s, op, dst, src, bb, nb, st, dot, ow);
+    case 6: return launch_bricks_n6(s, op, dst, src, bb, nb, st, dot, ow);
+    case 7: return launch_bricks_n7(s, op, dst, src, bb, nb, st, dot, ow);
+    case 8: return launch_bricks_n8(s, op, dst, src, bb, nb, st, dot, ow);
+    case 9: return launch_bricks_n9(s, op, dst, src, bb, nb, st, dot, ow);
+  }
+  set_error("unsupported degree %d", s.degree);
+  return B200MF_ERR_UNSUPPORTED;
+}
 
 static int launch_cells(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                         uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot) {
@@ -49,8 +71,34 @@ static int launch_cells(const Setup &s, const b200mf_operator &op, void *dst, co
 
 int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                      uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,
-                     double *dot_accum) {
-  return launch_cells(s, op, dst, src, cell_begin, cell_end, stream, false, dot_accum);
+                     double *dot_accum, bool dst_zeroed) {
+  // Cartesian cells + constant coefficients: whole bricks of cells go to the brick kernel,
+  // whatever is left of the range to the per-cell kernels (B200MF_KERNEL=v1|plane: A/B runs)
+  static const bool bricks_off = std::getenv("B200MF_KERNEL") != nullptr &&
+                                 std::string(std::getenv("B200MF_KERNEL")) != "brick";
+  if (s.n_bricks == 0 || bricks_off || op.grad_coefficient != nullptr || op.mass_coefficient != nullptr)
+    return launch_cells(s, op, dst, src, cell_begin, cell_end, stream, false, dot_accum);
+  const uint64_t W = (uint64_t)s.brick_b * s.brick_b * s.brick_b;
+  uint64_t pos = cell_begin;
+  for (const Setup::BrickRun &run : s.brick_runs) {
+    if (run.cell_end <= pos) continue;
+    if (run.cell_begin >= cell_end) break;
+    uint64_t rb = std::max(run.cell_begin, pos);
+    rb = run.cell_begin + (rb - run.cell_begin + W - 1) / W * W;
+    uint64_t re = std::min(run.cell_end, cell_end);
+    re = run.cell_begin + (re - run.cell_begin) / W * W;
+    if (re <= rb) continue;
+    if (pos < rb) {
+      int rc = launch_cells(s, op, dst, src, pos, rb, stream, false, dot_accum);
+      if (rc != B200MF_OK) return rc;
+    }
+    int rc = launch_bricks(s, op, dst, src, run.first_brick + (rb - run.cell_begin) / W, (re - rb) / W,
+                           stream, dot_accum, dst_zeroed);
+    if (rc != B200MF_OK) return rc;
+    pos = re;
+  }
+  if (pos < cell_end) return launch_cells(s, op, dst, src, pos, cell_end, stream, false, dot_accum);
+  return B200MF_OK;
 }
 
 int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *diag,
@@ -377,7 +425,7 @@ int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t s
 int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                cudaStream_t st, double *dot_accum) {
   B200MF_CUDA_CHECK(cudaMemsetAsync(dst, 0, (s.n_owned + s.n_ghost) * number_size(s.number), st));
-  int rc = launch_cell_loop(s, op, dst, src, 0, s.n_cells, st, dot_accum);
+  int rc = launch_cell_loop(s, op, dst, src, 0, s.n_cells, st, dot_accum, true);
   if (rc != B200MF_OK) return rc;
   return copy_constrained_impl(s, dst, src, st, dot_accum);
 }
@@ -506,6 +554,10 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
       else                        TRY(upload_converted<float>(&s.d_geom_table, table, s, &s.geometry_bytes));
       if (s.n_geom > 1)
         TRY(dev_alloc_copy<uint32_t>(&s.d_geom_id, geom_id.data(), geom_id.size(), s, &s.geometry_bytes));
+      if (s.cell_kind == B200MF_CELLS_CARTESIAN && s.n_geom == 1 && s.dim == 3) {
+        for (int i = 0; i < 4; ++i) s.geom0[i] = table[i];
+        TRY(build_bricks(*d, s));
+      }
     }
     // keep the vertices for quadrature point queries while they are small
     if (d->n_cells * nvd * 8 <= (512ull << 20)) {
@@ -559,7 +611,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   Setup *s = &h->impl;
   cudaFree(s->d_l2g); cudaFree(s->d_mask); cudaFree(s->d_geom_id); cudaFree(s->d_geom_table);
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
-  cudaFree(s->d_qpoints); cudaFree(s->d_scratch);
+  cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);
   for (void *w : s->d_stage) cudaFree(w);
@@ -575,6 +627,8 @@ int b200mf_setup_get_info(const b200mf_setup *h, b200mf_setup_info *info) {
   info->n_constrained_dofs = s.n_constrained; info->cell_kind = s.cell_kind;
   info->n_distinct_geometries = s.n_geom; info->device_bytes = s.device_bytes;
   info->geometry_bytes = s.geometry_bytes; info->index_bytes = s.index_bytes;
+  info->n_bricks = s.n_bricks;
+  info->cells_per_brick = (uint64_t)s.brick_b * s.brick_b * s.brick_b;
   return B200MF_OK;
 }
 

@@ -1,0 +1,283 @@
+// Brick kernel: the fast path of the operator kernel for Cartesian cells with constant
+// coefficients (the headline case: 3D Laplace / Helmholtz on a uniformly refined hyper_cube).
+//
+// Same operator as cell_loop_kernel / cell_loop_plane_kernel (ApplyKernel + FEEvaluation of
+// matrix_free/portable_matrix_free.templates.h:498-528, portable_fe_evaluation.h:363-745),
+// restructured around what bounds it on B200 (profiles/r01_plane_cell_loop_q4_f64_ncu.txt:
+// FP64 pipe 36 %, 2.35x the algorithmic DRAM traffic from index lists and atomics):
+//
+//  * A "brick" is an aligned window of b^3 cells that are consecutive in the (Morton-ordered)
+//    cell array and form a b x b x b block; its dofs form an L^3 lattice, L = b p + 1.  The
+//    setup (brick_setup.cpp) detects bricks from local_to_global alone and stores ONE index per
+//    lattice node (4 L^3 bytes per brick instead of 4 b^3 (p+1)^3), flagged "complete" when no
+//    cell outside the brick touches the dof.
+//  * One CTA gathers the lattice once (shared dofs are read once, not once per cell), and
+//    applies the operator to the whole brick as one macro element: on a Cartesian cell with a
+//    constant coefficient the cell matrix is  Kx (x) M (x) M + M (x) Ky (x) M + M (x) M (x) Kz'
+//    with the 1D mass matrix M = S W S^T and stiffness matrix K = (S D) W (S D)^T scaled by the
+//    cell's metric (and Kz' = Kz + c_mass det M), i.e. evaluate/quadrature/integrate collapse
+//    to 7 1D sweeps in nodal space instead of 12 sweeps through the quadrature points:
+//        A = Mx u, B = Kx u;   C = My A, D = Ky A + My B;   v = Kz' C + Mz D.
+//    One thread owns one lattice line per sweep (L^2 lines), walks its b cell blocks with the
+//    (p+1)x(p+1) matrices in even-odd form (both are symmetric and centro-symmetric) taken from
+//    the constant bank, and sums the shared end points of neighbouring blocks in registers: no
+//    scatter conflicts inside the brick, two lattice-sized shared-memory arrays, three CTA
+//    barriers per brick, all shared-memory accesses conflict free (lines are unit-stride across
+//    the threads, or L-strided with L odd).
+//  * Results of complete dofs (all of the lattice interior) are written with plain stores;
+//    only the brick surface uses atomics (RED.ADD): 1 - ((L-2)/(L-1))^3 of the dofs.
+#pragma once
+#include "cell_kernels.cuh"
+
+namespace b200mf {
+
+#define B200MF_MAP_COMPLETE 0x40000000u
+#define B200MF_MAP_INDEX 0x3fffffffu
+
+template <int p, int b, typename Number>
+struct BrickCfg {
+  static constexpr int n = p + 1;
+  static constexpr int L = b * p + 1;
+  static constexpr int L2 = L * L, L3 = L * L * L;
+  static constexpr int W = b * b * b; // cells per brick
+  static constexpr int threads = ((L2 + 31) / 32) * 32;
+  static constexpr size_t smem_bytes = 2 * sizeof(Number) * L3;
+  static constexpr int gather_iters = (L3 + threads - 1) / threads;
+};
+
+template <typename Number, int n>
+struct EoHalf { // even / odd parts of one input line
+  static constexpr int h = n / 2;
+  Number e[h > 0 ? h : 1], o[h > 0 ? h : 1], c;
+};
+
+template <typename Number, int n>
+__device__ __forceinline__ void eo_split(const Number (&in)[n], EoHalf<Number, n> &x) {
+  constexpr int h = n / 2;
+#pragma unroll
+  for (int i = 0; i < h; ++i) {
+    x.e[i] = in[i] + in[n - 1 - i];
+    x.o[i] = in[i] - in[n - 1 - i];
+  }
+  x.c = (n % 2) ? in[h] : Number(0);
+}
+
+template <typename Number, int n>
+struct EoAcc { // even / odd parts of one output line
+  static constexpr int h = n / 2, hq = (n + 1) / 2;
+  Number X[hq], Y[h > 0 ? h : 1];
+};
+
+// acc (=, +=) Mat * x
+template <bool first, typename Number, int n>
+__device__ __forceinline__ void eo_mac(const EoMatrix<Number, n> &M, const EoHalf<Number, n> &x,
+                                       EoAcc<Number, n> &acc) {
+  constexpr int h = n / 2, hq = (n + 1) / 2;
+#pragma unroll
+  for (int q = 0; q < hq; ++q) {
+    Number X = first ? M.E[q] * x.e[0] : acc.X[q] + M.E[q] * x.e[0];
+#pragma unroll
+    for (int i = 1; i < h; ++i) X += M.E[i * hq + q] * x.e[i];
+    if (n % 2) X += M.mid[q] * x.c;
+    acc.X[q] = X;
+  }
+#pragma unroll
+  for (int q = 0; q < h; ++q) {
+    Number Y = first ? M.O[q] * x.o[0] : acc.Y[q] + M.O[q] * x.o[0];
+#pragma unroll
+    for (int i = 1; i < h; ++i) Y += M.O[i * h + q] * x.o[i];
+    acc.Y[q] = Y;
+  }
+}
+
+template <typename Number, int n>
+__device__ __forceinline__ void eo_join(const EoAcc<Number, n> &acc, Number (&out)[n]) {
+  constexpr int h = n / 2;
+#pragma unroll
+  for (int q = 0; q < h; ++q) {
+    out[q] = acc.X[q] + acc.Y[q];
+    out[n - 1 - q] = acc.X[q] - acc.Y[q];
+  }
+  if (n % 2) out[h] = acc.X[h];
+}
+
+template <int p, typename Number>
+struct BrickKernelParams {
+  BrickMatrices<Number, p + 1> mat;
+  const uint32_t *map; // [n_bricks][L^3]: local dof index | B200MF_MAP_COMPLETE | B200MF_L2G_CONSTRAINED
+  const Number *src;
+  Number *dst;
+  double *dot_accum; // optional: += src . (A src) over these bricks
+  unsigned long long brick_begin;
+  int overwrite; // 1: dst is known to be zero (vmult) -> complete dofs are stored, not added
+};
+
+template <int p, int b, typename Number, bool DOT>
+__global__ void __launch_bounds__(BrickCfg<p, b, Number>::threads)
+brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm) {
+  using Cfg = BrickCfg<p, b, Number>;
+  constexpr int n = p + 1, L = Cfg::L, L2 = Cfg::L2, L3 = Cfg::L3, T = Cfg::threads;
+  constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED;
+  extern __shared__ __align__(16) unsigned char brick_smem[];
+  Number *P0 = reinterpret_cast<Number *>(brick_smem);
+  Number *P1 = P0 + L3;
+  const int tid = threadIdx.x;
+  const uint32_t *__restrict__ map = prm.map + (prm.brick_begin + blockIdx.x) * (unsigned long long)L3;
+  const Number *__restrict__ src = prm.src;
+
+  // ---- read_dof_values of the whole brick: every lattice node once
+  {
+    uint32_t idx[Cfg::gather_iters];
+#pragma unroll
+    for (int k = 0; k < Cfg::gather_iters; ++k) {
+      const int e = tid + k * T;
+      idx[k] = (e < L3) ? __ldg(map + e) : CBIT;
+    }
+    Number val[Cfg::gather_iters];
+#pragma unroll
+    for (int k = 0; k < Cfg::gather_iters; ++k)
+      val[k] = (idx[k] & CBIT) ? Number(0) : __ldg(src + (idx[k] & B200MF_MAP_INDEX));
+#pragma unroll
+    for (int k = 0; k < Cfg::gather_iters; ++k) {
+      const int e = tid + k * T;
+      if (e < L3) P0[e] = val[k];
+    }
+  }
+  __syncthreads();
+
+  const bool active = tid < L2;
+  const int la = tid % L, lb = tid / L;
+
+  // ---- x sweep: A = Mx u -> P0 (in place), B = Kx u -> P1; thread <-> (y, z)
+  if (active) {
+    Number *l0 = P0 + L * tid, *l1 = P1 + L * tid;
+    Number in[n], cA = Number(0), cB = Number(0);
+    in[0] = l0[0];
+#pragma unroll
+    for (int c = 0; c < b; ++c) {
+#pragma unroll
+      for (int k = 1; k < n; ++k) in[k] = l0[c * p + k];
+      EoHalf<Number, n> x;
+      eo_split<Number, n>(in, x);
+      EoAcc<Number, n> a;
+      Number oA[n], oB[n];
+      eo_mac<true, Number, n>(prm.mat.M, x, a);
+      eo_join<Number, n>(a, oA);
+      eo_mac<true, Number, n>(prm.mat.Kx, x, a);
+      eo_join<Number, n>(a, oB);
+      if (c > 0) { oA[0] += cA; oB[0] += cB; }
+#pragma unroll
+      for (int k = 0; k < p; ++k) {
+        l0[c * p + k] = oA[k];
+        l1[c * p + k] = oB[k];
+      }
+      cA = oA[p];
+      cB = oB[p];
+      in[0] = in[p];
+    }
+    l0[L - 1] = cA;
+    l1[L - 1] = cB;
+  }
+  __syncthreads();
+
+  // ---- y sweep: C = My A -> P0, D = Ky A + My B -> P1 (both in place); thread <-> (x, z)
+  if (active) {
+    Number *l0 = P0 + la + L2 * lb, *l1 = P1 + la + L2 * lb;
+    Number inA[n], inB[n], cC = Number(0), cD = Number(0);
+    inA[0] = l0[0];
+    inB[0] = l1[0];
+#pragma unroll
+    for (int c = 0; c < b; ++c) {
+#pragma unroll
+      for (int k = 1; k < n; ++k) {
+        inA[k] = l0[(c * p + k) * L];
+        inB[k] = l1[(c * p + k) * L];
+      }
+      EoHalf<Number, n> xa, xb;
+      eo_split<Number, n>(inA, xa);
+      eo_split<Number, n>(inB, xb);
+      EoAcc<Number, n> a;
+      Number oC[n], oD[n];
+      eo_mac<true, Number, n>(prm.mat.M, xa, a);
+      eo_join<Number, n>(a, oC);
+      eo_mac<true, Number, n>(prm.mat.Ky, xa, a);
+      eo_mac<false, Number, n>(prm.mat.M, xb, a);
+      eo_join<Number, n>(a, oD);
+      if (c > 0) { oC[0] += cC; oD[0] += cD; }
+#pragma unroll
+      for (int k = 0; k < p; ++k) {
+        l0[(c * p + k) * L] = oC[k];
+        l1[(c * p + k) * L] = oD[k];
+      }
+      cC = oC[p];
+      cD = oD[p];
+      inA[0] = inA[p];
+      inB[0] = inB[p];
+    }
+    l0[(L - 1) * L] = cC;
+    l1[(L - 1) * L] = cD;
+  }
+  __syncthreads();
+
+  // ---- z sweep: v = Kz' C + Mz D, written straight to dst; thread <-> (x, y)
+  double dot = 0.0;
+  if (active) {
+    const Number *l0 = P0 + tid, *l1 = P1 + tid;
+    const uint32_t *__restrict__ lm = map + tid;
+    Number *__restrict__ dst = prm.dst;
+    auto emit = [&](uint32_t m, Number v, Number u) {
+      if (!(m & CBIT)) {
+        Number *d = dst + (m & B200MF_MAP_INDEX);
+        if (m & B200MF_MAP_COMPLETE) *d = prm.overwrite ? v : *d + v;
+        else atomicAdd(d, v);
+        if (DOT) dot += double(u) * double(v);
+      }
+    };
+    Number inC[n], inD[n], cV = Number(0);
+    inC[0] = l0[0];
+    inD[0] = l1[0];
+#pragma unroll
+    for (int c = 0; c < b; ++c) {
+      uint32_t mi[p];
+      Number ui[p];
+#pragma unroll
+      for (int k = 0; k < p; ++k) mi[k] = __ldg(lm + (c * p + k) * L2);
+      if (DOT) {
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+          ui[k] = (mi[k] & CBIT) ? Number(0) : __ldg(src + (mi[k] & B200MF_MAP_INDEX));
+      }
+#pragma unroll
+      for (int k = 1; k < n; ++k) {
+        inC[k] = l0[(c * p + k) * L2];
+        inD[k] = l1[(c * p + k) * L2];
+      }
+      EoHalf<Number, n> xc, xd;
+      eo_split<Number, n>(inC, xc);
+      eo_split<Number, n>(inD, xd);
+      EoAcc<Number, n> a;
+      Number oV[n];
+      eo_mac<true, Number, n>(prm.mat.Kz, xc, a);
+      eo_mac<false, Number, n>(prm.mat.M, xd, a);
+      eo_join<Number, n>(a, oV);
+      if (c > 0) oV[0] += cV;
+#pragma unroll
+      for (int k = 0; k < p; ++k) emit(mi[k], oV[k], DOT ? ui[k] : Number(0));
+      cV = oV[p];
+      inC[0] = inC[p];
+      inD[0] = inD[p];
+    }
+    {
+      const uint32_t m = __ldg(lm + (L - 1) * L2);
+      Number u = Number(0);
+      if (DOT && !(m & CBIT)) u = __ldg(src + (m & B200MF_MAP_INDEX));
+      emit(m, cV, u);
+    }
+  }
+  if (DOT && prm.dot_accum != nullptr) {
+    dot = block_sum(dot);
+    if (tid == 0) atomicAdd(prm.dot_accum, dot);
+  }
+}
+
+} // namespace b200mf

@@ -1,0 +1,123 @@
+// Brick detection (setup side of brick_kernel.cuh): finds the aligned windows of b^3
+// consecutive cells whose local_to_global lists fit together as a b x b x b block of a
+// Morton-ordered mesh, and builds one index per lattice node for them.
+//
+// Plays the role of the index compression of the reference's CPU MatrixFree
+// (internal::MatrixFreeFunctions::DoFInfo::IndexStorageVariants, matrix_free/dof_info.h:95-180:
+// "interleaved_contiguous" & friends compress the per-cell index lists when the numbering
+// allows) for the device path: the only input is the index list the reference's setup
+// produces (portable_matrix_free.templates.h:292-298), no mesh topology.
+#include <algorithm>
+#include <cstring>
+
+#include "internal.h"
+
+namespace b200mf {
+
+namespace {
+inline void morton_decode(unsigned c, int &x, int &y, int &z) {
+  x = y = z = 0;
+  for (int k = 0; k < 3; ++k) {
+    x |= ((c >> (3 * k)) & 1u) << k;
+    y |= ((c >> (3 * k + 1)) & 1u) << k;
+    z |= ((c >> (3 * k + 2)) & 1u) << k;
+  }
+}
+} // namespace
+
+// Fills s.brick_* ; returns B200MF_OK also when no brick was found.
+int build_bricks(const b200mf_setup_desc &d, Setup &s) {
+  constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, COMPLETE = 0x40000000u, UNSET = 0xffffffffu;
+  s.n_bricks = 0;
+  s.brick_runs.clear();
+  if (s.dim != 3 || s.cell_kind != B200MF_CELLS_CARTESIAN || s.any_mask || s.n_geom != 1) return B200MF_OK;
+  const uint64_t n_total = s.n_owned + s.n_ghost;
+  if (n_total >= COMPLETE) return B200MF_OK;
+  const int p = s.degree, n = s.n, b = brick_edge(s.degree);
+  const int L = b * p + 1, L2 = L * L;
+  const uint64_t L3 = (uint64_t)L2 * L, W = (uint64_t)b * b * b, npc = (uint64_t)n * n * n;
+  const uint64_t n_windows = s.n_cells / W;
+  if (n_windows == 0) return B200MF_OK;
+  const uint32_t *l2g = d.local_to_global;
+
+  // how many (cell, local dof) pairs reference every dof
+  std::vector<uint8_t> count(n_total, 0);
+  const int64_t n_entries = (int64_t)(s.n_cells * npc);
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < n_entries; ++e) {
+    const uint32_t v = l2g[e];
+    if (!(v & CBIT) && v < n_total) {
+      // saturating at 255 (a dof referenced by > 254 local cells is simply never "complete")
+      uint8_t old = __atomic_load_n(&count[v], __ATOMIC_RELAXED);
+      while (old != 255 &&
+             !__atomic_compare_exchange_n(&count[v], &old, (uint8_t)(old + 1), true, __ATOMIC_RELAXED,
+                                          __ATOMIC_RELAXED)) {
+      }
+    }
+  }
+
+  std::vector<uint32_t> maps;
+  try {
+    maps.resize(n_windows * L3);
+  } catch (const std::bad_alloc &) {
+    return B200MF_OK; // no bricks: the per-cell kernels serve the whole mesh
+  }
+  std::vector<uint8_t> ok(n_windows, 0);
+  // position of the cells of a window in the block, and multiplicity of a lattice coordinate
+  std::vector<int> cx(W), cy(W), cz(W), mult(L);
+  for (unsigned c = 0; c < W; ++c) morton_decode(c, cx[c], cy[c], cz[c]);
+  for (int X = 0; X < L; ++X) mult[X] = (X % p == 0 && X > 0 && X < L - 1) ? 2 : 1;
+
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t w = 0; w < (int64_t)n_windows; ++w) {
+    uint32_t *lat = maps.data() + (uint64_t)w * L3;
+    std::fill(lat, lat + L3, UNSET);
+    bool good = true;
+    for (unsigned c = 0; c < W && good; ++c) {
+      const uint32_t *cl = l2g + ((uint64_t)w * W + c) * npc;
+      const int ox = cx[c] * p, oy = cy[c] * p, oz = cz[c] * p;
+      for (int k = 0; k < n && good; ++k)
+        for (int j = 0; j < n && good; ++j)
+          for (int i = 0; i < n; ++i) {
+            uint32_t v = cl[i + n * (j + n * k)];
+            if (v & CBIT) v = CBIT;
+            else if (v >= n_total) { good = false; break; }
+            uint32_t &slot = lat[(ox + i) + L * ((oy + j) + L * (oz + k))];
+            if (slot == UNSET) slot = v;
+            else if (slot != v) { good = false; break; }
+          }
+    }
+    if (!good) continue;
+    for (int Z = 0; Z < L; ++Z)
+      for (int Y = 0; Y < L; ++Y)
+        for (int X = 0; X < L; ++X) {
+          uint32_t &v = lat[X + L * (Y + L * Z)];
+          if (v == CBIT) continue;
+          if (count[v] == mult[X] * mult[Y] * mult[Z]) v |= COMPLETE;
+        }
+    ok[w] = 1;
+  }
+
+  // compact the maps of the accepted windows and record the runs of consecutive bricks
+  uint64_t nb = 0;
+  for (uint64_t w = 0; w < n_windows; ++w) {
+    if (!ok[w]) continue;
+    if (nb != w) std::memmove(maps.data() + nb * L3, maps.data() + w * L3, L3 * sizeof(uint32_t));
+    if (!s.brick_runs.empty() && s.brick_runs.back().cell_end == w * W)
+      s.brick_runs.back().cell_end = (w + 1) * W;
+    else
+      s.brick_runs.push_back({w * W, (w + 1) * W, nb});
+    ++nb;
+  }
+  if (nb == 0) return B200MF_OK;
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_brick_map, nb * L3 * sizeof(uint32_t)));
+  B200MF_CUDA_CHECK(cudaMemcpy(s.d_brick_map, maps.data(), nb * L3 * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice));
+  s.n_bricks = nb;
+  s.brick_b = b;
+  s.device_bytes += nb * L3 * sizeof(uint32_t);
+  s.index_bytes += nb * L3 * sizeof(uint32_t);
+  return B200MF_OK;
+}
+
+} // namespace b200mf

@@ -5,6 +5,7 @@
 
 #include "cell_kernels.cuh"
 #include "cell_kernels_plane.cuh"
+#include "brick_kernel.cuh"
 
 #ifndef B200MF_N
 #error "compile with -DB200MF_N=<degree+1>"
@@ -128,6 +129,33 @@ int launch_n(const Setup &s, const b200mf_operator &op, void *dst, const void *s
                                 : launch_kind<3, n, float>(s, op, dst, src, b, e, st, diag, dot);
 }
 
+template <int p, typename Number, bool DOT>
+int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                      uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
+                      bool overwrite) {
+  constexpr int b = brick_edge(p);
+  using Cfg = BrickCfg<p, b, Number>;
+  BrickKernelParams<p, Number> prm;
+  fill_brick_matrices<Number, p + 1>(s, op, prm.mat);
+  prm.map = s.d_brick_map;
+  prm.src = static_cast<const Number *>(src);
+  prm.dst = static_cast<Number *>(dst);
+  prm.dot_accum = dot_accum;
+  prm.brick_begin = brick_begin;
+  prm.overwrite = overwrite ? 1 : 0;
+  auto kernel = brick_cartesian_kernel<p, b, Number, DOT>;
+  static bool configured = false;
+  if (!configured) {
+    B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg::smem_bytes));
+    configured = true;
+  }
+  kernel<<<(unsigned)n_bricks, Cfg::threads, Cfg::smem_bytes, stream>>>(prm);
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
 } // namespace
 
 #define B200MF_CAT2(a, b) a##b
@@ -138,5 +166,18 @@ int B200MF_CAT(launch_cells_n, B200MF_N)(const Setup &s, const b200mf_operator &
                                          cudaStream_t st, bool diag, double *dot) {
   return launch_n<B200MF_N>(s, op, dst, src, b, e, st, diag, dot);
 }
+
+#if B200MF_N <= 9
+int B200MF_CAT(launch_bricks_n, B200MF_N)(const Setup &s, const b200mf_operator &op, void *dst,
+                                          const void *src, uint64_t brick_begin, uint64_t n_bricks,
+                                          cudaStream_t st, double *dot, bool ow) {
+  constexpr int p = B200MF_N - 1;
+  if (s.number == B200MF_F64)
+    return dot ? launch_bricks_one<p, double, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow)
+               : launch_bricks_one<p, double, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow);
+  return dot ? launch_bricks_one<p, float, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow)
+             : launch_bricks_one<p, float, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow);
+}
+#endif
 
 } // namespace b200mf

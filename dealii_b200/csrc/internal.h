@@ -37,6 +37,10 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
 
 constexpr int kMaxN = 9; // degree <= 8
 constexpr int kL2gPadCells = 16; // >= cells per warp of every plane-kernel configuration
+// cells per direction of a brick: b^3 consecutive cells of a Morton-ordered mesh form a block;
+// chosen so that the two lattice arrays of brick_kernel.cuh leave room for >= 2 CTAs per SM
+// where possible (one for degree 5 in FP64)
+constexpr int brick_edge(int degree) { return degree <= 2 ? 8 : degree <= 5 ? 4 : 2; }
 
 // Even-odd packed 1D matrix for out[q] = sum_i M[i][q] in[i] with
 // M[n-1-i][n-1-q] = +/- M[i][q]  (cf. shape_info.templates.h:1153-1180 convert_to_eo).
@@ -61,6 +65,13 @@ struct ShapeData {
   EoMatrix<Number, n> DtW; // Dt with the quadrature weight of the input point folded in
   Number w[n];            // 1D quadrature weights
   Number w2[n * n];       // w[a] * w[b] at [a * n + b]
+};
+
+// 1D matrices of the brick kernel (brick_kernel.cuh): reference mass matrix and the three
+// metric-scaled stiffness matrices, packed with sym = +1
+template <typename Number, int n>
+struct BrickMatrices {
+  EoMatrix<Number, n> M, Kx, Ky, Kz;
 };
 
 // Layout of the merged metric of general cells: rows of n quadrature points along x hold
@@ -109,6 +120,15 @@ struct Setup {
   bool any_mask = false;
   uint64_t device_bytes = 0, geometry_bytes = 0, index_bytes = 0;
 
+  // bricks (brick_kernel.cuh / brick_setup.cpp): one index per lattice node of every aligned
+  // window of brick_b^3 consecutive cells that forms a block; runs of consecutive bricks
+  struct BrickRun { uint64_t cell_begin, cell_end, first_brick; };
+  uint32_t *d_brick_map = nullptr;
+  uint64_t n_bricks = 0;
+  int brick_b = 0;
+  std::vector<BrickRun> brick_runs;
+  double geom0[4] = {0, 0, 0, 0}; // cartesian metric diagonal + det of the single-geometry mesh
+
   // scratch for reductions / solver
   double *d_scratch = nullptr;
   double *h_pinned = nullptr;
@@ -131,11 +151,20 @@ int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t s
 // kernels_dispatch.cu
 int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                      uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,
-                     double *dot_accum);
+                     double *dot_accum, bool dst_zeroed = false);
 int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *diag,
                             cudaStream_t stream);
 
+// brick_setup.cpp
+int build_bricks(const b200mf_setup_desc &d, Setup &s);
+// kernels: the bricks [brick_begin, brick_begin + n_bricks) of the setup
+int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                  uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
+                  bool overwrite);
+
 // shape.cpp
+template <typename Number, int n>
+void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrices<Number, n> &out);
 void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
                            std::vector<double> &q_points, std::vector<double> &subface);

@@ -170,7 +170,60 @@ void fill_shape_data(const Setup &s, ShapeData<Number, n> &out) {
     for (int b = 0; b < n; ++b) out.w2[a * n + b] = Number(s.q_weights[a] * s.q_weights[b]);
 }
 
+// 1D mass and stiffness matrices of the reference cell in the nodal basis,
+//   M[i][j] = sum_q w_q phi_i(x_q) phi_j(x_q),  K[i][j] = sum_q w_q phi_i'(x_q) phi_j'(x_q),
+// phi_i'(x_q) = sum_r S[i][r] D[r][q] (the collocation derivative is exact for degree p), scaled
+// by the metric of the mesh's single Cartesian cell shape and the operator's constants:
+//   A_cell = g (m0 K(x)M(x)M + m1 M(x)K(x)M + m2 M(x)M(x)K) + c det M(x)M(x)M
+template <typename Number, int n>
+void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrices<Number, n> &out) {
+  const double *S = s.shape_values.data(), *D = s.shape_grad_colloc.data(), *w = s.q_weights.data();
+  double G[n * n], M[n * n], K[n * n];
+  for (int i = 0; i < n; ++i)
+    for (int q = 0; q < n; ++q) {
+      double g = 0.0;
+      for (int r = 0; r < n; ++r) g += S[i * n + r] * D[r * n + q];
+      G[i * n + q] = g;
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double m = 0.0, k = 0.0;
+      for (int q = 0; q < n; ++q) {
+        m += w[q] * S[i * n + q] * S[j * n + q];
+        k += w[q] * G[i * n + q] * G[j * n + q];
+      }
+      M[i * n + j] = m;
+      K[i * n + j] = k;
+    }
+  // exact symmetry and centro-symmetry (round-off only)
+  auto symmetrise = [&](double *A) {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        const int i2 = n - 1 - i, j2 = n - 1 - j;
+        const double a = 0.25 * (A[i * n + j] + A[j * n + i] + A[i2 * n + j2] + A[j2 * n + i2]);
+        A[i * n + j] = A[j * n + i] = A[i2 * n + j2] = A[j2 * n + i2] = a;
+      }
+  };
+  symmetrise(M);
+  symmetrise(K);
+  const double g = op.grad_constant;
+  const bool has_mass = op.mass_coefficient != nullptr || op.mass_constant != 0.0;
+  const double cm = has_mass ? op.mass_constant * s.geom0[3] : 0.0;
+  double Kx[n * n], Ky[n * n], Kz[n * n];
+  for (int i = 0; i < n * n; ++i) {
+    Kx[i] = g * s.geom0[0] * K[i];
+    Ky[i] = g * s.geom0[1] * K[i];
+    Kz[i] = g * s.geom0[2] * K[i] + cm * M[i];
+  }
+  pack_eo<Number, n>(M, false, out.M);
+  pack_eo<Number, n>(Kx, false, out.Kx);
+  pack_eo<Number, n>(Ky, false, out.Ky);
+  pack_eo<Number, n>(Kz, false, out.Kz);
+}
+
 #define INST(N)                                                                     \
+  template void fill_brick_matrices<double, N>(const Setup &, const b200mf_operator &, BrickMatrices<double, N> &); \
+  template void fill_brick_matrices<float, N>(const Setup &, const b200mf_operator &, BrickMatrices<float, N> &);   \
   template void fill_shape_data<double, N>(const Setup &, ShapeData<double, N> &);  \
   template void fill_shape_data<float, N>(const Setup &, ShapeData<float, N> &);
 INST(2) INST(3) INST(4) INST(5) INST(6) INST(7) INST(8) INST(9)

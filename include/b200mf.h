@@ -120,6 +120,10 @@ typedef struct {
   uint64_t n_distinct_geometries; /* affine compression table size                       */
   uint64_t device_bytes;          /* total device memory owned by the setup              */
   uint64_t geometry_bytes, index_bytes;
+  /* cells served by the brick kernel: n_bricks aligned windows of cells_per_brick consecutive
+   * cells that form a block of a Morton-ordered Cartesian mesh (index lists compressed to
+   * one entry per lattice node, cf. DoFInfo::IndexStorageVariants, matrix_free/dof_info.h) */
+  uint64_t n_bricks, cells_per_brick;
 } b200mf_setup_info;
 int b200mf_setup_get_info(const b200mf_setup *s, b200mf_setup_info *info);
 
