@@ -180,6 +180,14 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
   }
   __syncthreads();
 
+  // the indices of this thread's z line (the scatter targets): requested now, used after the
+  // y sweep, so the z sweep never waits for them
+  uint32_t mz[L];
+  if (active) {
+#pragma unroll
+    for (int z = 0; z < L; ++z) mz[z] = __ldg(map + tid + z * L2);
+  }
+
   // ---- y sweep: C = My A -> P0, D = Ky A + My B -> P1 (both in place); thread <-> (x, z)
   if (active) {
     Number *l0 = P0 + la + L2 * lb, *l1 = P1 + la + L2 * lb;
@@ -223,12 +231,13 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
   double dot = 0.0;
   if (active) {
     const Number *l0 = P0 + tid, *l1 = P1 + tid;
-    const uint32_t *__restrict__ lm = map + tid;
     Number *__restrict__ dst = prm.dst;
-    auto emit = [&](uint32_t m, Number v, Number u) {
+    // emit(): complete dofs are stored (vmult: dst is zero) or stored after adding the old value
+    // (cell_loop adds into dst), everything else goes through RED.ADD
+    auto emit = [&](uint32_t m, Number v, Number u, Number o) {
       if (!(m & CBIT)) {
         Number *d = dst + (m & B200MF_MAP_INDEX);
-        if (m & B200MF_MAP_COMPLETE) *d = prm.overwrite ? v : *d + v;
+        if (m & B200MF_MAP_COMPLETE) *d = v + o;
         else atomicAdd(d, v);
         if (DOT) dot += double(u) * double(v);
       }
@@ -238,14 +247,18 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
     inD[0] = l1[0];
 #pragma unroll
     for (int c = 0; c < b; ++c) {
-      uint32_t mi[p];
-      Number ui[p];
-#pragma unroll
-      for (int k = 0; k < p; ++k) mi[k] = __ldg(lm + (c * p + k) * L2);
+      Number ui[p], old[p];
       if (DOT) {
 #pragma unroll
         for (int k = 0; k < p; ++k)
-          ui[k] = (mi[k] & CBIT) ? Number(0) : __ldg(src + (mi[k] & B200MF_MAP_INDEX));
+          ui[k] = (mz[c * p + k] & CBIT) ? Number(0) : __ldg(src + (mz[c * p + k] & B200MF_MAP_INDEX));
+      }
+      if (!prm.overwrite) {
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+          old[k] = (mz[c * p + k] & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE
+                       ? dst[mz[c * p + k] & B200MF_MAP_INDEX]
+                       : Number(0);
       }
 #pragma unroll
       for (int k = 1; k < n; ++k) {
@@ -262,16 +275,20 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
       eo_join<Number, n>(a, oV);
       if (c > 0) oV[0] += cV;
 #pragma unroll
-      for (int k = 0; k < p; ++k) emit(mi[k], oV[k], DOT ? ui[k] : Number(0));
+      for (int k = 0; k < p; ++k)
+        emit(mz[c * p + k], oV[k], DOT ? ui[k] : Number(0), prm.overwrite ? Number(0) : old[k]);
       cV = oV[p];
       inC[0] = inC[p];
       inD[0] = inD[p];
     }
     {
-      const uint32_t m = __ldg(lm + (L - 1) * L2);
+      const uint32_t m = mz[L - 1];
       Number u = Number(0);
       if (DOT && !(m & CBIT)) u = __ldg(src + (m & B200MF_MAP_INDEX));
-      emit(m, cV, u);
+      Number o = Number(0);
+      if (!prm.overwrite && (m & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE)
+        o = dst[m & B200MF_MAP_INDEX];
+      emit(m, cV, u, o);
     }
   }
   if (DOT && prm.dot_accum != nullptr) {

@@ -1,5 +1,7 @@
 """Tiny driver for ncu captures: a few vmults of one configuration."""
-import sys, torch, dealii_b200
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, dealii_b200
 dim, degree, ref, number = 3, int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 amp = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 mesh = dealii_b200.HyperCubeMesh(dim, degree, refinements=ref, deformation_amplitude=amp)
