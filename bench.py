@@ -56,9 +56,12 @@ def parse_args():
     return ap.parse_args()
 
 
-def kernel_name(args):
-    """The kernel the dispatch policy of csrc/cell_inst.cu picks for this workload."""
+def kernel_name(args, n_bricks=0):
+    """The kernel the dispatch policy of csrc/api.cu / cell_inst.cu picks for this workload."""
     n, f64, general = args.degree + 1, args.number == "f64", args.deformation != 0.0
+    if n_bricks and not general and os.environ.get("B200MF_KERNEL") in (None, "brick"):
+        b = 8 if args.degree <= 2 else 4 if args.degree <= 5 else 2
+        return f"brick_cartesian_kernel<{args.degree},{b},{'double' if f64 else 'float'}>"
     plane = (n <= 4 if f64 else (n <= 3 or n == 5)) if general else n <= 5
     if os.environ.get("B200MF_KERNEL") == "v1":
         plane = False
@@ -259,13 +262,14 @@ def run_engine(args):
     value = n_total / (ms_per_step * 1e-3) / 1e9
 
     # ---- roofline: the cell-loop kernel alone (CUDA events on its stream)
+    # (the launch vmult makes: the cell loop over all local cells in "dst was zeroed" mode)
     reps = max(args.steps, 10)
     for _ in range(3):
-        mf.cell_loop(op.op, src, dst)
+        mf.vmult_range(op.op, dst, src, 0, mesh.n_cells)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(reps):
-        mf.cell_loop(op.op, src, dst)
+        mf.vmult_range(op.op, dst, src, 0, mesh.n_cells)
     e1.record()
     torch.cuda.synchronize()
     ms_kernel = e0.elapsed_time(e1) / reps
@@ -279,7 +283,9 @@ def run_engine(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                "kernel": kernel_name(args),
+                "kernel": kernel_name(args, int(mf.info.n_bricks)),
+                "cells_in_bricks": int(mf.info.n_bricks * mf.info.cells_per_brick),
+                "cells": int(mesh.n_cells),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_dof": bpd, "peak_source": peak_src,
                 "note": ("FP64 sum factorisation is co-bound by the FP64 pipe (37.1 TFLOP/s measured, "
                          "tools/fp64_peak.cu); see DESIGN.md")}

@@ -676,6 +676,15 @@ int b200mf_cell_loop_range_dot(const b200mf_setup *h, const b200mf_operator *op,
   return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream, dot_accum);
 }
 
+int b200mf_vmult_range(const b200mf_setup *h, const b200mf_operator *op, void *dst,
+                       const void *src, uint64_t cell_begin, uint64_t cell_end,
+                       double *dot_accum, void *stream) {
+  B200MF_REQUIRE(h && op && dst && src, "null argument");
+  B200MF_REQUIRE(cell_begin <= cell_end && cell_end <= h->impl.n_cells, "bad cell range");
+  return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream,
+                          dot_accum, true);
+}
+
 int b200mf_copy_constrained_values_dot(const b200mf_setup *h, void *dst, const void *src,
                                        double *dot_accum, void *stream) {
   B200MF_REQUIRE(h && dst && src, "null argument");

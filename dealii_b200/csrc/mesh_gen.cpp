@@ -461,15 +461,23 @@ int b200mf_mesh_create_partitioned(const b200mf_partition_desc *pd, b200mf_mesh 
       if (is_boundary[i]) m->boundary.push_back((uint32_t)i);
   }
 
-  // ---- cell lists: interior cells (no ghost dof) first, Morton order kept inside each class
+  // ---- cell lists: interior cells (no ghost dof) first, Morton order kept inside each class.
+  // In 3D the classification is done for whole aligned blocks of b^3 consecutive cells (the
+  // bricks of brick_kernel.cuh, b = brick_edge(degree)): a block is "interior" if none of its
+  // cells touches a ghost dof, so both classes keep their bricks intact.
   const uint64_t nc = g.chunk;
   std::vector<uint64_t> order(nc);
   {
-    std::vector<uint64_t> boundary_cells;
-    uint64_t ni = 0;
-    for (uint64_t c = 0; c < nc; ++c) {
+    uint64_t W = 1;
+    if (dim == 3) {
+      const uint64_t b = (uint64_t)brick_edge(p);
+      if (nc % (b * b * b) == 0 && ((uint64_t)me * g.chunk) % (b * b * b) == 0) W = b * b * b;
+    }
+    std::vector<uint8_t> touches(nc, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (int64_t)nc; ++c) {
       int ijk[3];
-      global_cell_coords(g, (uint64_t)me * g.chunk + c, ijk);
+      global_cell_coords(g, (uint64_t)me * g.chunk + (uint64_t)c, ijk);
       bool touches_ghost = false;
       if (m->n_ghost) {
         // a cell touches a non-owned dof iff one of its 2^dim corner points is not owned
@@ -482,8 +490,17 @@ int b200mf_mesh_create_partitioned(const b200mf_partition_desc *pd, b200mf_mesh 
         }
         // faces/edges on a low interface without a ghost corner cannot exist for box partitions
       }
-      if (touches_ghost) boundary_cells.push_back(c);
-      else order[ni++] = c;
+      touches[c] = touches_ghost ? 1 : 0;
+    }
+    std::vector<uint64_t> boundary_cells;
+    uint64_t ni = 0;
+    for (uint64_t blk = 0; blk < nc / W; ++blk) {
+      bool any = false;
+      for (uint64_t c = blk * W; c < (blk + 1) * W; ++c) any |= touches[c] != 0;
+      for (uint64_t c = blk * W; c < (blk + 1) * W; ++c) {
+        if (any) boundary_cells.push_back(c);
+        else order[ni++] = c;
+      }
     }
     m->n_cells_interior = ni;
     for (uint64_t c : boundary_cells) order[ni++] = c;

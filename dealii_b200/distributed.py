@@ -239,12 +239,10 @@ class DistributedMatrixFree:
     def _range(self, op, dst, src, a, b, dot):
         if b <= a:
             return
+        # pieces of one vmult: dst was zeroed by vmult() below and nothing else writes it
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if dot is None:
-            L.check(self._lib.b200mf_cell_loop_range(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b, st))
-        else:
-            L.check(self._lib.b200mf_cell_loop_range_dot(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b,
-                                                         C.c_void_p(dot), st))
+        L.check(self._lib.b200mf_vmult_range(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b,
+                                             C.c_void_p(dot) if dot is not None else None, st))
 
     def vmult(self, op, dst, src, dot_ptr=None):
         """dst = A src on distributed vectors: ghost update || interior cells, cells at the
