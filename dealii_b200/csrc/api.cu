@@ -69,14 +69,23 @@ static int launch_cells(const Setup &s, const b200mf_operator &op, void *dst, co
   return B200MF_ERR_UNSUPPORTED;
 }
 
+static bool bricks_enabled(const Setup &s, const b200mf_operator &op) {
+  static const bool bricks_off = std::getenv("B200MF_KERNEL") != nullptr &&
+                                 std::string(std::getenv("B200MF_KERNEL")) != "brick";
+  return s.n_bricks != 0 && !bricks_off && op.grad_coefficient == nullptr && op.mass_coefficient == nullptr;
+}
+
+static bool selective_zero(const Setup &s, const b200mf_operator &op) {
+  static const bool full_memset = std::getenv("B200MF_FULL_MEMSET") != nullptr;
+  return bricks_enabled(s, op) && s.have_zero_list && !full_memset;
+}
+
 int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                      uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,
                      double *dot_accum, bool dst_zeroed) {
   // Cartesian cells + constant coefficients: whole bricks of cells go to the brick kernel,
   // whatever is left of the range to the per-cell kernels (B200MF_KERNEL=v1|plane: A/B runs)
-  static const bool bricks_off = std::getenv("B200MF_KERNEL") != nullptr &&
-                                 std::string(std::getenv("B200MF_KERNEL")) != "brick";
-  if (s.n_bricks == 0 || bricks_off || op.grad_coefficient != nullptr || op.mass_coefficient != nullptr)
+  if (!bricks_enabled(s, op))
     return launch_cells(s, op, dst, src, cell_begin, cell_end, stream, false, dot_accum);
   const uint64_t W = (uint64_t)s.brick_b * s.brick_b * s.brick_b;
   uint64_t pos = cell_begin;
@@ -87,6 +96,15 @@ int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const
     rb = run.cell_begin + (rb - run.cell_begin + W - 1) / W * W;
     uint64_t re = std::min(run.cell_end, cell_end);
     re = run.cell_begin + (re - run.cell_begin) / W * W;
+    if (dst_zeroed && selective_zero(s, op) &&
+        (rb != std::max(run.cell_begin, pos) || re != std::min(run.cell_end, cell_end))) {
+      // the dofs a brick stores were not zeroed by b200mf_vmult_prepare: its cells must not be
+      // split over pieces (they would be added by the per-cell kernels)
+      set_error("vmult piece [%llu, %llu) cuts a brick of %llu cells: align the pieces of a vmult to "
+                "b200mf_setup_info.cells_per_brick", (unsigned long long)cell_begin,
+                (unsigned long long)cell_end, (unsigned long long)W);
+      return B200MF_ERR_INVALID;
+    }
     if (re <= rb) continue;
     if (pos < rb) {
       int rc = launch_cells(s, op, dst, src, pos, rb, stream, false, dot_accum);
@@ -422,9 +440,27 @@ int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t s
   return B200MF_OK;
 }
 
+int vmult_prepare_impl(const Setup &s, const b200mf_operator &op, void *dst, cudaStream_t st) {
+  if (selective_zero(s, op)) {
+    // the brick kernel stores every dof that only one brick touches: zero the others
+    if (s.n_zero_list == 0) return B200MF_OK;
+    const unsigned blocks = (unsigned)((s.n_zero_list + 255) / 256);
+    if (s.number == B200MF_F64)
+      set_constrained_kernel<double><<<blocks, 256, 0, st>>>((double *)dst, 0.0, s.d_zero_list, s.n_zero_list);
+    else
+      set_constrained_kernel<float><<<blocks, 256, 0, st>>>((float *)dst, 0.0f, s.d_zero_list, s.n_zero_list);
+    count_launch();
+    B200MF_CUDA_CHECK(cudaGetLastError());
+    return B200MF_OK;
+  }
+  B200MF_CUDA_CHECK(cudaMemsetAsync(dst, 0, (s.n_owned + s.n_ghost) * number_size(s.number), st));
+  return B200MF_OK;
+}
+
 int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                cudaStream_t st, double *dot_accum) {
-  B200MF_CUDA_CHECK(cudaMemsetAsync(dst, 0, (s.n_owned + s.n_ghost) * number_size(s.number), st));
+  int rc0 = vmult_prepare_impl(s, op, dst, st);
+  if (rc0 != B200MF_OK) return rc0;
   int rc = launch_cell_loop(s, op, dst, src, 0, s.n_cells, st, dot_accum, true);
   if (rc != B200MF_OK) return rc;
   return copy_constrained_impl(s, dst, src, st, dot_accum);
@@ -611,7 +647,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   Setup *s = &h->impl;
   cudaFree(s->d_l2g); cudaFree(s->d_mask); cudaFree(s->d_geom_id); cudaFree(s->d_geom_table);
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
-  cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map);
+  cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map); cudaFree(s->d_zero_list);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);
   for (void *w : s->d_stage) cudaFree(w);
@@ -674,6 +710,11 @@ int b200mf_cell_loop_range_dot(const b200mf_setup *h, const b200mf_operator *op,
   B200MF_REQUIRE(h && op && dst && src, "null argument");
   B200MF_REQUIRE(cell_begin <= cell_end && cell_end <= h->impl.n_cells, "bad cell range");
   return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream, dot_accum);
+}
+
+int b200mf_vmult_prepare(const b200mf_setup *h, const b200mf_operator *op, void *dst, void *stream) {
+  B200MF_REQUIRE(h && op && dst, "null argument");
+  return vmult_prepare_impl(h->impl, *op, dst, (cudaStream_t)stream);
 }
 
 int b200mf_vmult_range(const b200mf_setup *h, const b200mf_operator *op, void *dst,

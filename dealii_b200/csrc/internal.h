@@ -125,6 +125,10 @@ struct Setup {
   struct BrickRun { uint64_t cell_begin, cell_end, first_brick; };
   uint32_t *d_brick_map = nullptr;
   uint64_t n_bricks = 0;
+  // dofs vmult has to zero before its cell loop (all that no brick stores); valid if have_zero_list
+  uint32_t *d_zero_list = nullptr;
+  uint64_t n_zero_list = 0;
+  bool have_zero_list = false;
   int brick_b = 0;
   std::vector<BrickRun> brick_runs;
   double geom0[4] = {0, 0, 0, 0}; // cartesian metric diagonal + det of the single-geometry mesh
@@ -146,6 +150,8 @@ int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void 
                cudaStream_t stream, double *dot_accum);
 int copy_constrained_impl(const Setup &s, void *dst, const void *src, cudaStream_t st,
                           double *dot_accum);
+// the "dst = 0" of vmult for a cell loop that runs in dst-was-zeroed mode
+int vmult_prepare_impl(const Setup &s, const b200mf_operator &op, void *dst, cudaStream_t st);
 int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t st);
 
 // kernels_dispatch.cu

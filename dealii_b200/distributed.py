@@ -229,6 +229,10 @@ class DistributedMatrixFree:
         self.n_cells, self.n_interior = mesh.n_cells, mesh.n_cells_interior
         self.comm_stream = torch.cuda.Stream(device=self.mf.device)
         self._lib = L.load()
+        # the interior/boundary split must not cut a brick for the store-instead-of-add pieces
+        w = int(self.mf.info.cells_per_brick) if self.mf.info.n_bricks else 1
+        self._brick_cells = max(w, 1)
+        self._pieces_aligned = self.n_interior % self._brick_cells == 0
 
     def initialize_dof_vector(self):
         return self.mf.initialize_dof_vector()
@@ -241,8 +245,12 @@ class DistributedMatrixFree:
             return
         # pieces of one vmult: dst was zeroed by vmult() below and nothing else writes it
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        L.check(self._lib.b200mf_vmult_range(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b,
-                                             C.c_void_p(dot) if dot is not None else None, st))
+        dp = C.c_void_p(dot) if dot is not None else None
+        if self._pieces_aligned:
+            L.check(self._lib.b200mf_vmult_range(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b, dp, st))
+        else:
+            L.check(self._lib.b200mf_cell_loop_range_dot(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b,
+                                                         dp, st))
 
     def vmult(self, op, dst, src, dot_ptr=None):
         """dst = A src on distributed vectors: ghost update || interior cells, cells at the
@@ -251,11 +259,16 @@ class DistributedMatrixFree:
         main = torch.cuda.current_stream()
         ex, ni, nc = self.exchange, self.n_interior, self.n_cells
         single = self.partitioner.n_ranks == 1 or (not ex.ghost_slices and not ex.import_slices)
-        dst.zero_()
+        if self._pieces_aligned:
+            L.check(self._lib.b200mf_vmult_prepare(self.mf._h, C.byref(op), _ptr(dst),
+                                                   C.c_void_p(main.cuda_stream)))   # dst = 0 where needed
+        else:
+            dst.zero_()
         if single:
             self._range(op, dst, src, 0, nc, dot_ptr)
         else:
-            half = ni // 2 if self.overlap else 0
+            w = self._brick_cells
+            half = (ni // 2) // w * w if self.overlap else 0    # pieces of a vmult never cut a brick
             self.comm_stream.wait_stream(main)
             with torch.cuda.stream(self.comm_stream):
                 works = ex.update_ghost_values_start(src)

@@ -194,6 +194,9 @@ class MatrixFree:
     def vmult(self, op, dst, src):
         L.check(self._lib.b200mf_vmult(self._h, C.byref(op), _ptr(dst), _ptr(src), _stream()))
 
+    def vmult_prepare(self, op, dst):
+        L.check(self._lib.b200mf_vmult_prepare(self._h, C.byref(op), _ptr(dst), _stream()))
+
     def vmult_range(self, op, dst, src, cell_begin, cell_end, dot_ptr=None):
         """One piece of a vmult (dst zeroed by the caller before the first piece)."""
         L.check(self._lib.b200mf_vmult_range(self._h, C.byref(op), _ptr(dst), _ptr(src), cell_begin,

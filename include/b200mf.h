@@ -249,11 +249,15 @@ int b200mf_cell_loop_range_dot(const b200mf_setup *s, const b200mf_operator *op,
 int b200mf_copy_constrained_values_dot(const b200mf_setup *s, void *dst, const void *src,
                                        double *dot_accum, void *stream);
 /* One piece of a vmult over the local cells [cell_begin, cell_end): b200mf_cell_loop_range_dot
- * for callers that zeroed dst themselves before the first piece and let nothing else write it
+ * for callers that zeroed dst (b200mf_vmult_prepare) before the first piece and let nothing else write it
  * until the last piece is enqueued (distributed_cell_loop's interior / boundary pieces,
  * portable_matrix_free.templates.h:1602-1656, after the dst = 0 of the operator's vmult).  With
  * that guarantee the engine stores (instead of adds) the dofs only one brick of cells touches.
  * dot_accum may be NULL.                                                                     */
+/* The "dst = 0" that precedes those pieces: zeroes at least every entry of dst (owned and ghost)
+ * that the pieces accumulate into -- all of dst, or only the dofs on brick surfaces when the
+ * brick kernel serves the operator and stores everything else.                                */
+int b200mf_vmult_prepare(const b200mf_setup *s, const b200mf_operator *op, void *dst, void *stream);
 int b200mf_vmult_range(const b200mf_setup *s, const b200mf_operator *op, void *dst,
                        const void *src, uint64_t cell_begin, uint64_t cell_end,
                        double *dot_accum, void *stream);

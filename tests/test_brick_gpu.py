@@ -157,3 +157,28 @@ def test_no_bricks_on_lexicographic_cell_order():
     mesh = dealii_b200.HyperCubeMesh(3, 4, subdivisions=4)
     mf = dealii_b200.MatrixFree("f64").reinit_from_mesh(mesh)
     assert mf.info.n_bricks == 0
+
+
+@pytest.mark.parametrize("selective", [False, True])
+def test_vmult_pieces_and_selective_zeroing(selective, monkeypatch):
+    """b200mf_vmult_prepare + brick-aligned b200mf_vmult_range pieces == vmult, starting from a dst
+    full of garbage.  With B200MF_SELECTIVE_ZERO only the dofs no brick stores are zeroed, and a
+    piece that cuts a brick is refused."""
+    if selective:
+        monkeypatch.setenv("B200MF_SELECTIVE_ZERO", "1")
+    else:
+        monkeypatch.delenv("B200MF_SELECTIVE_ZERO", raising=False)
+    om, oracle, mf, op = make(4, 3, "f64", dirichlet=True, cpu_mf=True, mass=2.0)
+    src = np.random.default_rng(17).random(om.n_dofs)
+    ref = oracle.vmult_cpu_matrixfree(src)
+    x = torch.from_numpy(src).cuda()
+    y = torch.full((om.n_dofs,), 1.0e300, dtype=torch.float64, device="cuda")
+    mf.vmult_prepare(op.op, y)
+    for a, b in ((0, 128), (320, 512), (128, 320)):
+        mf.vmult_range(op.op, y, x, a, b)
+    mf.copy_constrained_values(x, y)
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu().numpy(), ref) < 1e-12
+    if selective:
+        with pytest.raises(L.B200MFError):
+            mf.vmult_range(op.op, y, x, 0, 100)
