@@ -178,7 +178,7 @@ def run_reference(args):
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(args, n_dofs_total, parallelism):
@@ -205,6 +205,11 @@ def run_engine(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's version / debug banner goes to stdout by default: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the ghost exchange must get SM slots while the cell-loop kernel has CTAs queued
+        # (tools/dist_diag.py: 2-GPU vmult 1.28 -> 1.18 ms with the NCCL stream at high priority)
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
 
@@ -350,9 +355,10 @@ def run_engine(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "cg": cg,
                 "e2e_matches_device": bool(check < 1e-12)}
-        print(json.dumps(line), flush=True)
+    result = line if rank == 0 else None
     if world > 1:
         dist.destroy_process_group()
+    return result
 
 
 def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
@@ -391,9 +397,27 @@ def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
             "api": "dealii_b200.distributed.solve_cg (b200mf_cg_* kernels + all-reduce of the CG scalars)"}
 
 
+class StdoutForJsonOnly:
+    """Library banners (e.g. "NCCL version ..." printed by libnccl to fd 1) must not mix with the
+    one JSON line of the contract: route fd 1 to stderr while the benchmark runs, restore it for
+    the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_engine(a)
+    with StdoutForJsonOnly() as guard:
+        line = run_reference(a) if a.impl == "reference" else run_engine(a)
+    if line is not None:
+        print(json.dumps(line), flush=True)

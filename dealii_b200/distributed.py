@@ -16,8 +16,17 @@ Mirrors, by name and meaning:
 Pack / unpack-add, the operator and the CG vector updates are CUDA kernels of libb200mf.so;
 transport is NCCL point-to-point (ncclSend/ncclRecv grouped per exchange) over NVLink, issued
 on a side stream so that interior cells run while the ghost values are in flight.
+
+Overlap needs the transfer kernels to get SM slots while the cell loop has thousands of CTAs
+queued: create the process group with TORCH_NCCL_HIGH_PRIORITY=1 in the environment (set below
+as a default; it is read when the NCCL process group is created).  Measured with
+tools/dist_diag.py on 2 x B200, Q4 FP64, 135 M DoFs per GPU: vmult 1.28 ms without, 1.18 ms with
+(local cell loop alone: 1.13 ms).
 """
 import ctypes as C
+import os
+
+os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
 
 import numpy as np
 import torch
@@ -171,6 +180,20 @@ class GhostExchange:
             self.import_slices.append((r, off, off + c))
             off += c
         self._lib = L.load() if self.device.type == "cuda" else None
+        # NCCL: one all_to_all_single per exchange (a grouped ncclSend/ncclRecv issued from C++)
+        # instead of 2 x n_neighbours Python-level P2POps -- the host cost of the latter (7
+        # neighbours on a 2x2x2 box) was what bounded the 8-GPU vmult.  Ghosts are sorted by global
+        # index = by owner rank, the import buffer by importing rank: both are split by rank.
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.ghost_splits, self.import_splits = [0] * world, [0] * world
+        for r, c in p.ghost_targets:
+            self.ghost_splits[r] = int(c)
+        for r, c in p.import_targets:
+            self.import_splits[r] = int(c)
+        ranks_sorted = (sorted(r for r, _ in p.ghost_targets) == [r for r, _ in p.ghost_targets] and
+                        sorted(r for r, _ in p.import_targets) == [r for r, _ in p.import_targets])
+        self._use_a2a = (self.device.type == "cuda" and dist.is_initialized() and world > 1 and
+                         dist.get_backend(group) == "nccl" and ranks_sorted)
 
     # -- kernels (CUDA only: the product has no CPU path)
     def _pack(self, vec):
@@ -182,6 +205,17 @@ class GhostExchange:
                                                   self.part.n_import, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def _transfer(self, vec, to_ghosts):
+        if self._use_a2a:
+            p = self.part
+            ghost = vec[p.n_owned:p.n_owned + p.n_ghost]
+            packed = self.buf[:p.n_import]
+            if to_ghosts:
+                w = dist.all_to_all_single(ghost, packed, self.ghost_splits, self.import_splits,
+                                           group=self.group, async_op=True)
+            else:
+                w = dist.all_to_all_single(packed, ghost, self.import_splits, self.ghost_splits,
+                                           group=self.group, async_op=True)
+            return [w]
         ops = []
         for r, a, b in self.ghost_slices:          # my ghost section <-> its owner
             ops.append(dist.P2POp(dist.irecv if to_ghosts else dist.isend, vec[a:b], r, group=self.group))
@@ -227,7 +261,9 @@ class DistributedMatrixFree:
         self.exchange = GhostExchange(self.partitioner, number, device, group)
         self.n_owned, self.n_ghost = mesh.n_owned, mesh.n_ghost
         self.n_cells, self.n_interior = mesh.n_cells, mesh.n_cells_interior
-        self.comm_stream = torch.cuda.Stream(device=self.mf.device)
+        # high priority: the pack / unpack kernels and (with TORCH_NCCL_HIGH_PRIORITY=1, see the
+        # module docstring) NCCL's transfer kernels take SM slots as CTAs of the cell loop retire
+        self.comm_stream = torch.cuda.Stream(device=self.mf.device, priority=-1)
         self._lib = L.load()
         # the interior/boundary split must not cut a brick for the store-instead-of-add pieces
         w = int(self.mf.info.cells_per_brick) if self.mf.info.n_bricks else 1
