@@ -712,6 +712,24 @@ int b200mf_cell_loop_range_dot(const b200mf_setup *h, const b200mf_operator *op,
   return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream, dot_accum);
 }
 
+int b200mf_brick_probe(const b200mf_setup_desc *d, uint64_t *n_bricks, uint64_t *cells_per_brick,
+                       uint64_t *n_complete_dofs) {
+  B200MF_REQUIRE(d && n_bricks && cells_per_brick && n_complete_dofs, "null argument");
+  B200MF_REQUIRE(d->dim == 3 && d->degree >= 1 && d->degree <= 8 && d->local_to_global, "bad descriptor");
+  Setup s;
+  s.dim = d->dim; s.degree = d->degree; s.n = d->degree + 1; s.number = d->number;
+  s.n_cells = d->n_cells; s.n_owned = d->n_owned_dofs; s.n_ghost = d->n_ghost_dofs;
+  s.cell_kind = B200MF_CELLS_CARTESIAN; s.n_geom = 1; // the probe looks at the index lists only
+  if (d->constraint_mask)
+    for (uint64_t c = 0; c < d->n_cells; ++c)
+      if (d->constraint_mask[c]) s.any_mask = true;
+  *n_complete_dofs = 0;
+  int rc = build_bricks(*d, s, false, n_complete_dofs);
+  *n_bricks = s.n_bricks;
+  *cells_per_brick = (uint64_t)s.brick_b * s.brick_b * s.brick_b;
+  return rc;
+}
+
 int b200mf_vmult_prepare(const b200mf_setup *h, const b200mf_operator *op, void *dst, void *stream) {
   B200MF_REQUIRE(h && op && dst, "null argument");
   return vmult_prepare_impl(h->impl, *op, dst, (cudaStream_t)stream);

@@ -27,7 +27,7 @@ inline void morton_decode(unsigned c, int &x, int &y, int &z) {
 } // namespace
 
 // Fills s.brick_* ; returns B200MF_OK also when no brick was found.
-int build_bricks(const b200mf_setup_desc &d, Setup &s) {
+int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_complete_out) {
   constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, COMPLETE = 0x40000000u, UNSET = 0xffffffffu;
   s.n_bricks = 0;
   s.brick_runs.clear();
@@ -109,6 +109,17 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s) {
     else
       s.brick_runs.push_back({w * W, (w + 1) * W, nb});
     ++nb;
+  }
+  if (n_complete_out) {
+    uint64_t nc = 0;
+    for (uint64_t e = 0; e < nb * L3; ++e)
+      if (!(maps[e] & CBIT) && (maps[e] & COMPLETE)) ++nc;
+    *n_complete_out = nc;
+  }
+  if (!upload) { // host-only probe (b200mf_brick_probe): counts, no device arrays
+    s.n_bricks = nb;
+    s.brick_b = b;
+    return B200MF_OK;
   }
   if (nb == 0) return B200MF_OK;
   // vmult stores the complete dofs, so only the others have to be zeroed first.  Measured on

@@ -162,7 +162,8 @@ int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *dia
                             cudaStream_t stream);
 
 // brick_setup.cpp
-int build_bricks(const b200mf_setup_desc &d, Setup &s);
+int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload = true,
+                 uint64_t *n_complete_out = nullptr);
 // kernels: the bricks [brick_begin, brick_begin + n_bricks) of the setup
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                   uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,

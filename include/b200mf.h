@@ -127,6 +127,13 @@ typedef struct {
 } b200mf_setup_info;
 int b200mf_setup_get_info(const b200mf_setup *s, b200mf_setup_info *info);
 
+/* HOST-only probe of the brick detection the setup runs on the index lists (no device needed):
+ * how many aligned windows of cells_per_brick consecutive cells fit together as a block, and how
+ * many lattice nodes of those bricks are "complete" (touched by no cell outside their brick, so
+ * vmult stores them without atomics).  Geometry is not looked at.                             */
+int b200mf_brick_probe(const b200mf_setup_desc *desc, uint64_t *n_bricks, uint64_t *cells_per_brick,
+                       uint64_t *n_complete_dofs);
+
 /* Quadrature point coordinates, the input of PMF::evaluate_coefficients functors
  * (portable_matrix_free.h:585, get_quadrature_point :417): writes
  * out[(cell*n_q_total + q)*dim + d] to a HOST array. */
