@@ -549,6 +549,21 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
                                  &s.index_bytes));
   if (s.number == B200MF_F64) TRY(upload_converted<double>(&s.d_weights, s.subface, s, nullptr));
   else                        TRY(upload_converted<float>(&s.d_weights, s.subface, s, nullptr));
+  {
+    // tables of the sum-factorised diagonal: SS = S.*S, GG = (SD).*(SD), SG = S.*(SD), [i*n+q]
+    std::vector<double> tb(3 * n * n);
+    for (int i = 0; i < n; ++i)
+      for (int q = 0; q < n; ++q) {
+        double g = 0.0;
+        for (int r = 0; r < n; ++r) g += s.shape_values[i * n + r] * s.shape_grad_colloc[r * n + q];
+        const double sv = s.shape_values[i * n + q];
+        tb[i * n + q] = sv * sv;
+        tb[n * n + i * n + q] = g * g;
+        tb[2 * n * n + i * n + q] = sv * g;
+      }
+    if (s.number == B200MF_F64) TRY(upload_converted<double>(&s.d_diag_tables, tb, s, nullptr));
+    else                        TRY(upload_converted<float>(&s.d_diag_tables, tb, s, nullptr));
+  }
 
   // --- geometry
   double *d_qp = nullptr, *d_qw = nullptr;
@@ -647,6 +662,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   Setup *s = &h->impl;
   cudaFree(s->d_l2g); cudaFree(s->d_mask); cudaFree(s->d_geom_id); cudaFree(s->d_geom_table);
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
+  cudaFree(s->d_diag_tables);
   cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map); cudaFree(s->d_zero_list);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);

@@ -88,7 +88,14 @@ int launch_one(const Setup &s, const b200mf_operator &op, void *dst, const void 
       return B200MF_OK;
     }
   }
-  if (diagonal) {
+  if (diagonal && p.mask == nullptr && s.d_diag_tables != nullptr) {
+    // compute_diagonal by sum factorisation (see cell_kernels.cuh)
+    smem += sizeof(Number) * 3 * n * n;
+    auto kernel = cell_diagonal_sumfac_kernel<dim, n, Number, KIND>;
+    B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    kernel<<<grid, Cfg::threads, smem, stream>>>(p, static_cast<const Number *>(s.d_diag_tables));
+  } else if (diagonal) {
     smem += sizeof(Number) * Cfg::cells * Cfg::npc;
     auto kernel = cell_diagonal_kernel<dim, n, Number, KIND>;
     B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

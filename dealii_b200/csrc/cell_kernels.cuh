@@ -446,4 +446,143 @@ cell_diagonal_kernel(const __grid_constant__ CellKernelParams<dim, n, Number, KI
   }
 }
 
+// compute_diagonal by sum factorisation (cells without hanging-node masks).  With
+// phi_i(q) = prod_a S[i_a][q_a] and d_d phi_i(q) = (SD)[i_d][q_d] prod_{a != d} S[i_a][q_a],
+//   A_ii = sum_q sum_{d,e} M_de(q) d_d phi_i d_e phi_i + m(q) phi_i^2
+// is, term by term, the contraction of a coefficient field with a tensor product of the 1D tables
+// SS = S.*S, GG = (SD).*(SD), SG = S.*(SD): three sweeps per term, dim(dim+1)/2 + 1 terms, instead
+// of the (p+1)^dim operator applications of the reference (matrix_free/tools.h:1392-1569, whose
+// result it reproduces to round-off).  tables = [SS | GG | SG], each [i * n + q].
+template <int dim, int n, int dir, typename Number>
+__device__ __forceinline__ void plain_sweep(const Number *T, Number *A, int line) {
+  int base, stride;
+  line_geometry<dim, n, dir>(line, base, stride);
+  Number r[n], o[n];
+#pragma unroll
+  for (int k = 0; k < n; ++k) r[k] = A[base + k * stride];
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    Number acc = T[i * n] * r[0];
+#pragma unroll
+    for (int q = 1; q < n; ++q) acc += T[i * n + q] * r[q];
+    o[i] = acc;
+  }
+#pragma unroll
+  for (int k = 0; k < n; ++k) A[base + k * stride] = o[k];
+}
+
+template <int dim, int n, typename Number, int KIND>
+__global__ void __launch_bounds__(BlockCfg<dim, n>::threads)
+cell_diagonal_sumfac_kernel(const __grid_constant__ CellKernelParams<dim, n, Number, KIND> p,
+                            const Number *__restrict__ tables) {
+  using Cfg = BlockCfg<dim, n>;
+  constexpr int npc = Cfg::npc, NS = n_sym(dim), n2 = n * n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Number *sm = reinterpret_cast<Number *>(smem_raw);
+  Number *T = sm + Cfg::smem_elems; // [3][n*n]
+  const int tid = threadIdx.x;
+  const int cib = tid / Cfg::lines;
+  const int line = tid - cib * Cfg::lines;
+  const unsigned long long cell0 = p.cell_begin + (unsigned long long)blockIdx.x * Cfg::cells;
+  const unsigned long long remaining = p.cell_end - cell0;
+  const int ncell = remaining < (unsigned long long)Cfg::cells ? (int)remaining : Cfg::cells;
+  const bool active = cib < ncell;
+  const unsigned long long cell = cell0 + (active ? cib : 0);
+  Number *W = sm + (cib < Cfg::cells ? cib : 0) * Cfg::cell_stride; // work array of this cell
+  Number *Dg = W + npc;                                              // its diagonal
+  for (int i = tid; i < 3 * n2; i += Cfg::threads) T[i] = tables[i];
+  const Number *SS = T, *GG = T + n2, *SG = T + 2 * n2;
+
+  int base, stride;
+  line_geometry<dim, n, dim - 1>(line, base, stride);
+  Number wline;
+  if (dim == 2) wline = p.shape.w[line];
+  else          wline = p.shape.w[line % n] * p.shape.w[line / n];
+  Number m[NS], det = Number(1);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) m[s] = Number(0);
+  if (KIND != B200MF_CELLS_GENERAL && active) {
+    const unsigned gi = p.geom_id ? p.geom_id[cell] : 0u;
+    if (KIND == B200MF_CELLS_CARTESIAN) {
+      const Number *t = p.geom_table + gi * (dim + 1);
+      // diagonal entries of the symmetric storage: 2D (0, 2), 3D (0, 3, 5)
+      m[0] = t[0];
+      m[dim == 2 ? 2 : 3] = t[1];
+      if (dim == 3) m[5] = t[2];
+      det = t[dim];
+    } else {
+      const Number *t = p.geom_table + gi * (NS + 1);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) m[s] = t[s];
+      det = t[NS];
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < n; ++k) Dg[base + k * stride] = Number(0);
+  }
+  __syncthreads();
+
+  // terms: the NS entries (d <= e) of the metric, then the mass term
+  int s = 0;
+#pragma unroll
+  for (int d = 0; d < dim; ++d)
+#pragma unroll
+    for (int e = d; e <= dim; ++e) {
+      const bool mass = (e == dim);
+      if (mass && d != dim - 1) continue; // one mass term, attached to the last d
+      const bool skip = mass ? !p.op.has_mass : (KIND == B200MF_CELLS_CARTESIAN && d != e);
+      const int ss = s;
+      if (!mass) ++s;
+      if (skip) continue;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+          const int q = base + k * stride;
+          const unsigned long long gq = cell * npc + q;
+          Number c;
+          if (mass) {
+            Number cm = p.op.mass_const;
+            if (p.op.mass_coef) cm += p.op.mass_coef[gq];
+            const Number jxw = (KIND == B200MF_CELLS_GENERAL) ? p.jxw[gq] : det * wline * p.shape.w[k];
+            c = cm * jxw;
+          } else {
+            Number cg = p.op.grad_const * (d == e ? Number(1) : Number(2));
+            if (p.op.grad_coef) cg *= p.op.grad_coef[gq];
+            const Number mq = (KIND == B200MF_CELLS_GENERAL) ? p.metric[metric_offset<dim>(n, cell, ss, q)]
+                                                            : m[ss] * wline * p.shape.w[k];
+            c = cg * mq;
+          }
+          W[q] = c;
+        }
+      }
+      __syncthreads();
+      auto table = [&](int a) -> const Number * {
+        if (mass) return SS;
+        if (a == d && a == e) return GG;
+        if (a == d || a == e) return SG;
+        return SS;
+      };
+      if (active) plain_sweep<dim, n, 0>(table(0), W, line);
+      __syncthreads();
+      if (active) plain_sweep<dim, n, 1>(table(1), W, line);
+      __syncthreads();
+      if (dim == 3) {
+        if (active) plain_sweep<dim, n, (dim == 3 ? 2 : 0)>(table(2), W, line);
+        __syncthreads();
+      }
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) Dg[base + k * stride] += W[base + k * stride];
+      }
+      __syncthreads();
+    }
+  const uint32_t *l2g = p.l2g + cell0 * npc;
+  for (int i = tid; i < ncell * npc; i += Cfg::threads) {
+    const int c = i / npc, k = i - c * npc;
+    const uint32_t idx = l2g[i];
+    if (!(idx & B200MF_L2G_CONSTRAINED)) atomicAdd(p.dst + idx, sm[c * Cfg::cell_stride + npc + k]);
+  }
+}
+
 } // namespace b200mf

@@ -112,6 +112,7 @@ struct Setup {
   void *d_jxw = nullptr;           // general: [n_cells][n_q_total]
   uint32_t *d_constrained = nullptr;
   void *d_weights = nullptr;       // subface interpolation matrix [n*n] (Number)
+  void *d_diag_tables = nullptr;   // [SS | GG | SG] of the sum-factorised diagonal, each [n*n] (Number)
   double *d_qpoints = nullptr;     // optional cache
   // host copies needed later
   std::vector<double> shape_values, shape_grad_colloc, q_weights, q_points_1d, subface;
