@@ -38,9 +38,9 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
 constexpr int kMaxN = 9; // degree <= 8
 constexpr int kL2gPadCells = 16; // >= cells per warp of every plane-kernel configuration
 // cells per direction of a brick: b^3 consecutive cells of a Morton-ordered mesh form a block;
-// chosen so that the two lattice arrays of brick_kernel.cuh leave room for >= 2 CTAs per SM
-// where possible (one for degree 5 in FP64)
-constexpr int brick_edge(int degree) { return degree <= 2 ? 8 : degree <= 5 ? 4 : 2; }
+// chosen by measurement (Q3/Q4: b = 4 beats 2 by 20 %; Q5: b = 2 (L = 11, many small CTAs) beats
+// b = 4 (L = 21, one 148 KB CTA per SM) by 15 %)
+constexpr int brick_edge(int degree) { return degree <= 2 ? 8 : degree <= 4 ? 4 : 2; }
 
 // Even-odd packed 1D matrix for out[q] = sum_i M[i][q] in[i] with
 // M[n-1-i][n-1-q] = +/- M[i][q]  (cf. shape_info.templates.h:1153-1180 convert_to_eo).
