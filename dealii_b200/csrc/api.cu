@@ -37,6 +37,10 @@ DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 
+#define DECL_N(N) int debug_resolve_n##N(int, int, unsigned, int, double *);
+DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
+#undef DECL_N
+
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                   uint64_t bb, uint64_t nb, cudaStream_t st, double *dot, bool ow) {
   switch (s.n) {
@@ -726,6 +730,22 @@ int b200mf_cell_loop_range_dot(const b200mf_setup *h, const b200mf_operator *op,
   B200MF_REQUIRE(h && op && dst && src, "null argument");
   B200MF_REQUIRE(cell_begin <= cell_end && cell_end <= h->impl.n_cells, "bad cell range");
   return launch_cell_loop(h->impl, *op, dst, src, cell_begin, cell_end, (cudaStream_t)stream, dot_accum);
+}
+
+int b200mf_debug_resolve_hanging_nodes(int dim, int degree, int number, uint16_t constraint_mask,
+                                       int transpose, double *values_host) {
+  B200MF_REQUIRE(values_host && (dim == 2 || dim == 3) && degree >= 1 && degree <= 8, "bad argument");
+  B200MF_REQUIRE(number == B200MF_F64 || number == B200MF_F32, "bad number type");
+  switch (degree + 1) {
+    case 2: return debug_resolve_n2(dim, number, constraint_mask, transpose, values_host);
+    case 3: return debug_resolve_n3(dim, number, constraint_mask, transpose, values_host);
+    case 4: return debug_resolve_n4(dim, number, constraint_mask, transpose, values_host);
+    case 5: return debug_resolve_n5(dim, number, constraint_mask, transpose, values_host);
+    case 6: return debug_resolve_n6(dim, number, constraint_mask, transpose, values_host);
+    case 7: return debug_resolve_n7(dim, number, constraint_mask, transpose, values_host);
+    case 8: return debug_resolve_n8(dim, number, constraint_mask, transpose, values_host);
+    default: return debug_resolve_n9(dim, number, constraint_mask, transpose, values_host);
+  }
 }
 
 int b200mf_brick_probe(const b200mf_setup_desc *d, uint64_t *n_bricks, uint64_t *cells_per_brick,

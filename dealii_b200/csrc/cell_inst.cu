@@ -136,6 +136,43 @@ int launch_n(const Setup &s, const b200mf_operator &op, void *dst, const void *s
                                 : launch_kind<3, n, float>(s, op, dst, src, b, e, st, diag, dot);
 }
 
+// resolve_hanging_nodes of ONE cell, for the golden-vector test of the device code path
+template <int dim, int n, typename Number>
+__global__ void __launch_bounds__(BlockCfg<dim, n>::threads)
+resolve_hanging_nodes_kernel(Number *values, const Number *weights, unsigned mask, int transpose) {
+  using Cfg = BlockCfg<dim, n>;
+  constexpr int npc = Cfg::npc;
+  __shared__ Number U[npc];
+  const int tid = threadIdx.x;
+  const bool active = tid < Cfg::lines; // cell 0 of the CTA
+  for (int i = tid; i < npc; i += Cfg::threads) U[i] = values[i];
+  __syncthreads();
+  if (transpose) resolve_hanging_nodes_cell<dim, n, Number, true>(weights, mask, U, tid, active);
+  else           resolve_hanging_nodes_cell<dim, n, Number, false>(weights, mask, U, tid, active);
+  for (int i = tid; i < npc; i += Cfg::threads) values[i] = U[i];
+}
+
+template <int dim, int n, typename Number>
+int debug_resolve_one(unsigned mask, int transpose, double *values_host) {
+  constexpr int npc = BlockCfg<dim, n>::npc;
+  std::vector<double> sv, sg, qw, qp, sub;
+  build_fe_q_shape_data(n - 1, sv, sg, qw, qp, sub);
+  std::vector<Number> w(sub.begin(), sub.end()), v(values_host, values_host + npc);
+  Number *dw = nullptr, *dv = nullptr;
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&dw, sizeof(Number) * n * n));
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&dv, sizeof(Number) * npc));
+  B200MF_CUDA_CHECK(cudaMemcpy(dw, w.data(), sizeof(Number) * n * n, cudaMemcpyHostToDevice));
+  B200MF_CUDA_CHECK(cudaMemcpy(dv, v.data(), sizeof(Number) * npc, cudaMemcpyHostToDevice));
+  resolve_hanging_nodes_kernel<dim, n, Number><<<1, BlockCfg<dim, n>::threads>>>(dv, dw, mask, transpose);
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  B200MF_CUDA_CHECK(cudaMemcpy(v.data(), dv, sizeof(Number) * npc, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < npc; ++i) values_host[i] = double(v[i]);
+  cudaFree(dw);
+  cudaFree(dv);
+  return B200MF_OK;
+}
+
 template <int p, typename Number, bool DOT>
 int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                       uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
@@ -172,6 +209,15 @@ int B200MF_CAT(launch_cells_n, B200MF_N)(const Setup &s, const b200mf_operator &
                                          const void *src, uint64_t b, uint64_t e,
                                          cudaStream_t st, bool diag, double *dot) {
   return launch_n<B200MF_N>(s, op, dst, src, b, e, st, diag, dot);
+}
+
+int B200MF_CAT(debug_resolve_n, B200MF_N)(int dim, int number, unsigned mask, int transpose,
+                                          double *values_host) {
+  if (dim == 2)
+    return number == B200MF_F64 ? debug_resolve_one<2, B200MF_N, double>(mask, transpose, values_host)
+                                : debug_resolve_one<2, B200MF_N, float>(mask, transpose, values_host);
+  return number == B200MF_F64 ? debug_resolve_one<3, B200MF_N, double>(mask, transpose, values_host)
+                              : debug_resolve_one<3, B200MF_N, float>(mask, transpose, values_host);
 }
 
 #if B200MF_N <= 9

@@ -127,6 +127,14 @@ typedef struct {
 } b200mf_setup_info;
 int b200mf_setup_get_info(const b200mf_setup *s, b200mf_setup_info *info);
 
+/* Test hook: the device code path of Portable::internal::resolve_hanging_nodes
+ * (matrix_free/portable_hanging_nodes_internal.h:414-459) applied to the (degree+1)^dim values of
+ * ONE cell (HOST array, overwritten) for a ConstraintKinds mask; transpose != 0 applies the
+ * transposed interpolation.  This is what tests/matrix_free/hanging_node_kernels_01.cc exercises in
+ * the reference; the parity test feeds its golden vectors through this entry point.            */
+int b200mf_debug_resolve_hanging_nodes(int dim, int degree, int number, uint16_t constraint_mask,
+                                       int transpose, double *values_host);
+
 /* HOST-only probe of the brick detection the setup runs on the index lists (no device needed):
  * how many aligned windows of cells_per_brick consecutive cells fit together as a block, and how
  * many lattice nodes of those bricks are "complete" (touched by no cell outside their brick, so

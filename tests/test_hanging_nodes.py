@@ -66,3 +66,27 @@ def test_device_resolve_hanging_nodes(dim, case, degree, number):
     ref = conforming_apply(hm, oracle, u)
     err = np.abs(y.cpu().numpy().astype(np.float64) - ref).max() / np.abs(ref).max()
     assert err < (1e-12 if number == "f64" else 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("number", ["f64", "f32"])
+def test_device_kernel_reproduces_reference_golden_vectors(number):
+    """The reference's own known-answer test for this kernel
+    (tests/matrix_free/hanging_node_kernels_01.output, all 234 blocks) through the C ABI."""
+    import ctypes as C
+    import os
+    from dealii_b200 import _lib as L
+    from oracle.hanging_kernel import golden_cases, parse_golden
+    lib = L.load()
+    golden = os.path.join(os.path.dirname(__file__), "golden", "hanging_node_kernels_01.output")
+    groups = parse_golden(golden)
+    k = 0
+    for dim, degree, mask in golden_cases():
+        for transpose in (0, 1):
+            inp, ref, _ = groups[k]
+            k += 1
+            v = np.ascontiguousarray(inp, dtype=np.float64).copy()
+            L.check(lib.b200mf_debug_resolve_hanging_nodes(dim, degree, L.F64 if number == "f64" else L.F32,
+                                                           mask, transpose, v.ctypes.data_as(C.c_void_p)))
+            assert np.allclose(v, ref, rtol=2e-5, atol=2e-5), (dim, degree, mask, transpose)
+    assert k == 234

@@ -145,3 +145,23 @@ def test_shape_info_properties():
         np.testing.assert_allclose(s.shape_values @ s.shape_gradients_collocation,
                                    s.shape_gradients, atol=1e-11)
         np.testing.assert_allclose(s.subface_interpolation_matrix.sum(1), 1.0, atol=1e-13)
+
+
+def test_hanging_node_kernels_01():
+    """tests/matrix_free/hanging_node_kernels_01.output: the reference applies its hanging-node
+    interpolation (and the transpose) to values[i] = i for every face / edge mask, degrees 1-3,
+    2D and 3D; the numpy restatement of the device kernel reproduces all 234 blocks."""
+    from oracle.hanging_kernel import golden_cases, parse_golden, resolve_hanging_nodes
+    groups = parse_golden(os.path.join(GOLD, "hanging_node_kernels_01.output"))
+    cases = golden_cases()
+    assert len(groups) == 2 * len(cases) == 234
+    k = 0
+    for dim, degree, mask in cases:
+        W = ShapeInfo(degree).subface_interpolation_matrix
+        for transpose in (False, True):
+            inp, ref, opt = groups[k]
+            k += 1
+            assert np.array_equal(inp, np.arange((degree + 1) ** dim))
+            out = resolve_hanging_nodes(inp, mask, dim, degree, W, transpose)
+            assert np.allclose(out, ref, rtol=2e-5, atol=2e-5), (dim, degree, mask, transpose)
+            assert np.allclose(out, opt, rtol=2e-5, atol=2e-5)
