@@ -165,3 +165,30 @@ def test_hanging_node_kernels_01():
             out = resolve_hanging_nodes(inp, mask, dim, degree, W, transpose)
             assert np.allclose(out, ref, rtol=2e-5, atol=2e-5), (dim, degree, mask, transpose)
             assert np.allclose(out, opt, rtol=2e-5, atol=2e-5)
+
+
+def solver_cg_interleave_golden():
+    """(dim, degree, ||solution||_2, iterations) of tests/matrix_free/solver_cg_interleave.cc:
+    test<2>(3), test<3>(4), test<3>(3); the l2 norm and the iteration count do not depend on the
+    numbering or on the three ranks the reference ran on."""
+    txt = _read("solver_cg_interleave.mpirun=3.output")
+    norms = [float(x) for x in re.findall(r"CG solver with interleaving support\nDEAL::Norm of the solution: ([0-9.]+)", txt)]
+    calls = [int(x) for x in re.findall(r"CG solver with interleaving support\nDEAL::Norm of the solution: [0-9.]+\nDEAL::Number of calls to special vmult: (\d+)", txt)]
+    assert len(norms) == 3 and len(calls) == 3
+    return [(2, 3, norms[0], calls[0]), (3, 4, norms[1], calls[1]), (3, 3, norms[2], calls[2])]
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_solver_cg_interleave_norms_and_iterations(case):
+    """SolverCG + DiagonalMatrix on (grad u, grad v) + 10 (u, v), hyper_cube refine_global(6 - dim),
+    no constraints, rhs = 1/sqrt(N), preconditioner = 1 ./ (A rhs), tolerance 1e-2 ||rhs||."""
+    from oracle.solvers import solver_cg
+    dim, degree, norm, its = solver_cg_interleave_golden()[case]
+    m = HyperCubeMesh(dim, degree, refinements=6 - dim)
+    o = MatrixFreeOracle(m, mass_coefficient=10.0)
+    rhs = np.full(m.n_dofs, 1.0 / np.sqrt(m.n_dofs))
+    d = o.cell_loop(rhs)
+    r = solver_cg(o.cell_loop, rhs, DiagonalMatrix(np.where(d != 0, 1.0 / d, 0.0)),
+                  tol=1e-2 * np.linalg.norm(rhs), max_steps=200)
+    assert r["iterations"] == its
+    assert abs(np.linalg.norm(r["x"]) - norm) < 1e-7 * norm

@@ -94,3 +94,36 @@ def test_cg_fp32():
     control = dealii_b200.SolverControl(1000, 1e-5 * float(np.linalg.norm(ref["b"])))
     dealii_b200.SolverCG(control).solve(A, x, b, inv_diag)
     assert np.abs(x.cpu().numpy() - ref["x"]).max() < 1e-4 * np.abs(ref["x"]).max()
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_solver_cg_interleave_golden(case):
+    """The reference's known answers of tests/matrix_free/solver_cg_interleave.cc (golden output
+    solver_cg_interleave.with_p4est=true.mpirun=3.output): CG + DiagonalMatrix on
+    (grad u, grad v) + 10 (u, v), hyper_cube refine_global(6 - dim), rhs = 1/sqrt(N),
+    preconditioner = 1 ./ (A rhs), tolerance 1e-2 ||rhs||: solution norms 240.33305 / 3609.9220 /
+    1572.3941 and 51 / 61 / 39 operator applications inside the solver (3D cases: brick kernel)."""
+    import os
+    import re
+    with open(os.path.join(os.path.dirname(__file__), "golden", "solver_cg_interleave.mpirun=3.output")) as f:
+        txt = f.read()
+    found = re.findall(r"CG solver with interleaving support\nDEAL::Norm of the solution: ([0-9.]+)\n"
+                       r"DEAL::Number of calls to special vmult: (\d+)", txt)
+    assert len(found) == 3
+    dim, degree = [(2, 3), (3, 4), (3, 3)][case]
+    norm, its = float(found[case][0]), int(found[case][1])
+    mesh = dealii_b200.HyperCubeMesh(dim, degree, refinements=6 - dim)
+    mf = dealii_b200.MatrixFree("f64").reinit_from_mesh(mesh)
+    A = dealii_b200.MatrixFreeOperator(mf, grad_constant=1.0, mass_constant=10.0)
+    n = mf.n_owned
+    b = torch.full((n,), 1.0 / np.sqrt(n), dtype=torch.float64, device="cuda")
+    d = mf.initialize_dof_vector()
+    A.vmult(d, b)
+    inv = torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
+    x = mf.initialize_dof_vector()
+    control = dealii_b200.SolverControl(200, 1e-2 * float(b.norm()))
+    dealii_b200.SolverCG(control).solve(A, x, b, dealii_b200.DiagonalMatrix(inv))
+    assert abs(control.last_step() - its) <= 1
+    assert abs(float(x.norm()) - norm) < 2e-5 * norm   # stopped at 1e-2: +-1 iteration moves the norm
+    if control.last_step() == its:
+        assert abs(float(x.norm()) - norm) < 1e-7 * norm
