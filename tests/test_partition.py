@@ -7,6 +7,8 @@
   oracle's vmult with the oracle cell operator applied to each rank's local cells."""
 import os
 
+import re
+
 import numpy as np
 import pytest
 import torch
@@ -167,3 +169,32 @@ def test_gloo_two_ranks_ghost_exchange_and_vmult(dim, degree, refinements):
         assert np.abs(dst - expect).max() <= 1e-12 * np.abs(ref).max()
         covered += len(lat)
     assert covered == om.n_dofs
+
+
+def _parse_index_set(txt):
+    out = []
+    for tok in re.findall(r"\[(\d+),(\d+)\]|(\d+)", txt):
+        if tok[2]:
+            out.append(int(tok[2]))
+        else:
+            out += list(range(int(tok[0]), int(tok[1]) + 1))
+    return out
+
+
+def test_owned_and_relevant_sets_match_the_references_two_rank_run():
+    """tests/matrix_free_kokkos/matrix_free_device_initialize_vector (mpirun=2, p4est): 2D Q1 on
+    hyper_cube refine_global(2): the locally owned range and the locally relevant dofs
+    (= owned + the ghosts Portable::MatrixFree's partitioner holds) of both ranks, as printed by the
+    reference, against the partitioned mesh generator -- a real multi-rank known answer for the
+    "numbering and ghost index sets bit-exact" requirement."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "matrix_free_device_initialize_vector.mpirun=2.output")
+    txt = open(path).read()
+    blocks = re.findall(r"DEAL:(\d):\d::locally owned dofs :\n(\{.*\})\nDEAL:\d:\d::locally relevant dofs :\n(\{.*\})", txt)
+    assert len(blocks) == 4                                  # two vector types x two ranks
+    for rank_s, owned_s, relevant_s in blocks:
+        rank = int(rank_s)
+        owned, relevant = _parse_index_set(owned_s), _parse_index_set(relevant_s)
+        pm = PartitionedHyperCubeMesh(2, 1, refinements=2, n_ranks=2, rank=rank, ghost_mode="relevant")
+        assert owned == list(range(pm.first_owned_global, pm.first_owned_global + pm.n_owned))
+        assert sorted(set(relevant) - set(owned)) == sorted(np.asarray(pm.ghost_global).tolist())
