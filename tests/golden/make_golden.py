@@ -14,6 +14,7 @@ files = {
     "tests/matrix_free_kokkos/matrix_free_device_matrix_vector_03.output": "matrix_free_device_matrix_vector_03.output",
     "tests/matrix_free/step-37.with_lapack=true.output": "step-37.output",
     "tests/matrix_free/hanging_node_kernels_01.output": "hanging_node_kernels_01.output",
+    "tests/mpi/p4est_2d_dofhandler_01.mpirun=4.with_p4est=true.output": "p4est_2d_dofhandler_01.mpirun=4.output",
     "tests/matrix_free_kokkos/matrix_free_device_initialize_vector.with_mpi=on.with_p4est=on.mpirun=2.output":
         "matrix_free_device_initialize_vector.mpirun=2.output",
     "tests/matrix_free/solver_cg_interleave.with_p4est=true.mpirun=3.output": "solver_cg_interleave.mpirun=3.output",

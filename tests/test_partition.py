@@ -198,3 +198,35 @@ def test_owned_and_relevant_sets_match_the_references_two_rank_run():
         pm = PartitionedHyperCubeMesh(2, 1, refinements=2, n_ranks=2, rank=rank, ghost_mode="relevant")
         assert owned == list(range(pm.first_owned_global, pm.first_owned_global + pm.n_owned))
         assert sorted(set(relevant) - set(owned)) == sorted(np.asarray(pm.ghost_global).tolist())
+
+
+def test_global_numbering_matches_the_references_four_rank_run():
+    """tests/mpi/p4est_2d_dofhandler_01 (mpirun=4, p4est): 2D Q2 on hyper_cube refine_global(2).
+    The reference prints the owned dof counts of the four ranks and, for every cell rank 0 knows
+    (its own and its ghost cells, active-cell = Morton order), the GLOBAL dof indices in
+    hierarchical order.  Rebuilt here from the four ranks' partitioned meshes."""
+    import os
+    from oracle.mesh import hierarchic_to_lexicographic, morton_cell_coords
+    path = os.path.join(os.path.dirname(__file__), "golden", "p4est_2d_dofhandler_01.mpirun=4.output")
+    lines = [l.split("::", 1)[1].strip() for l in open(path) if "::" in l]
+    counts = [int(t) for t in lines[1].split()[1:]]
+    cell_lines = [[int(t) for t in l.split()] for l in lines[3:]]
+    meshes = [PartitionedHyperCubeMesh(2, 2, refinements=2, n_ranks=4, rank=r, ghost_mode="relevant")
+              for r in range(4)]
+    assert [m.n_owned for m in meshes] == counts
+    h2l = hierarchic_to_lexicographic(2, 2)
+    # global hierarchical index list of every cell, keyed by its integer coordinates
+    cells = {}
+    for m in meshes:
+        glob = np.concatenate((m.first_owned_global + np.arange(m.n_owned), np.asarray(m.ghost_global))).astype(np.int64)
+        for c in range(m.n_cells):
+            xy = tuple(np.round(m.cell_vertices[c, 0] * 4).astype(int))
+            cells[xy] = glob[m.l2g[c] & 0x7FFFFFFF][h2l]
+    assert len(cells) == 16
+    # rank 0 owns the first 4 cells of the Morton curve and sees the cells touching them
+    order = [tuple(c) for c in morton_cell_coords(2, 2)]
+    own = set(order[:4])
+    known = [c for c in order if c in own or any(abs(c[0] - o[0]) <= 1 and abs(c[1] - o[1]) <= 1 for o in own)]
+    assert len(known) == len(cell_lines) == 9
+    for c, expect in zip(known, cell_lines):
+        assert cells[c].tolist() == expect, c
