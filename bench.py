@@ -60,7 +60,7 @@ def kernel_name(args, n_bricks=0):
     """The kernel the dispatch policy of csrc/api.cu / cell_inst.cu picks for this workload."""
     n, f64, general = args.degree + 1, args.number == "f64", args.deformation != 0.0
     if n_bricks and not general and os.environ.get("B200MF_KERNEL") in (None, "brick"):
-        b = 8 if args.degree <= 2 else 4 if args.degree <= 4 else 2
+        b = 16 if args.degree == 1 else 8 if args.degree == 2 else 4 if args.degree <= 4 else 2
         return f"brick_cartesian_kernel<{args.degree},{b},{'double' if f64 else 'float'}>"
     plane = (n <= 4 if f64 else (n <= 3 or n == 5)) if general else n <= 5
     if os.environ.get("B200MF_KERNEL") == "v1":

@@ -18,7 +18,7 @@ namespace b200mf {
 namespace {
 inline void morton_decode(unsigned c, int &x, int &y, int &z) {
   x = y = z = 0;
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 4; ++k) { // brick edges up to 16 cells
     x |= ((c >> (3 * k)) & 1u) << k;
     y |= ((c >> (3 * k + 1)) & 1u) << k;
     z |= ((c >> (3 * k + 2)) & 1u) << k;

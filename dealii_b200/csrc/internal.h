@@ -38,9 +38,9 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
 constexpr int kMaxN = 9; // degree <= 8
 constexpr int kL2gPadCells = 16; // >= cells per warp of every plane-kernel configuration
 // cells per direction of a brick: b^3 consecutive cells of a Morton-ordered mesh form a block;
-// chosen by measurement (Q3/Q4: b = 4 beats 2 by 20 %; Q5: b = 2 (L = 11, many small CTAs) beats
+// chosen by measurement (Q1: b = 16 (L = 17) beats 8 by 20 % in FP64; Q3/Q4: b = 4 beats 2 by 20 %; Q5: b = 2 (L = 11, many small CTAs) beats
 // b = 4 (L = 21, one 148 KB CTA per SM) by 15 %)
-constexpr int brick_edge(int degree) { return degree <= 2 ? 8 : degree <= 4 ? 4 : 2; }
+constexpr int brick_edge(int degree) { return degree == 1 ? 16 : degree == 2 ? 8 : degree <= 4 ? 4 : 2; }
 
 // Even-odd packed 1D matrix for out[q] = sum_i M[i][q] in[i] with
 // M[n-1-i][n-1-q] = +/- M[i][q]  (cf. shape_info.templates.h:1153-1180 convert_to_eo).

@@ -23,7 +23,7 @@ def probe(degree, l2g, n_dofs, mask=None):
     return nb.value, cpb.value, ncomp.value
 
 
-@pytest.mark.parametrize("degree,refinements,b", [(1, 3, 8), (2, 3, 8), (3, 2, 4), (4, 3, 4), (5, 2, 2),
+@pytest.mark.parametrize("degree,refinements,b", [(1, 4, 16), (2, 3, 8), (3, 2, 4), (4, 3, 4), (5, 2, 2),
                                                   (6, 2, 2), (8, 1, 2)])
 def test_every_window_of_a_morton_hyper_cube_is_a_brick(degree, refinements, b):
     mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements)

@@ -25,8 +25,8 @@ def rel_err(a, ref):
 
 
 def brick_refinements(degree):
-    # smallest refine_global() that holds bricks: 8^3 cells for degree <= 2, 4^3 up to 4, then 2^3
-    return 3 if degree <= 2 else 2 if degree <= 4 else 1
+    # smallest refine_global() that holds bricks: 16^3 cells for degree 1, 8^3 for 2, 4^3 up to 4, then 2^3
+    return 4 if degree == 1 else 3 if degree == 2 else 2 if degree <= 4 else 1
 
 
 def make(degree, refinements, number, dirichlet=False, cpu_mf=False, mass=0.0, grad=1.0):

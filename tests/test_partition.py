@@ -81,7 +81,7 @@ def test_partitioned_numbering_matches_oracle(dim, degree, refinements, n_ranks,
             if dim == 2:
                 assert touches.all()
             else:
-                b = 8 if degree <= 2 else 4 if degree <= 4 else 2
+                b = 16 if degree == 1 else 8 if degree == 2 else 4 if degree <= 4 else 2
                 W = b ** 3 if pm.n_cells % b ** 3 == 0 else 1
                 assert touches.reshape(-1, W).any(axis=1).all()
         # lexicographic order inside a cell is preserved: x fastest lattice ids
