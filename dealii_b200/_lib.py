@@ -113,6 +113,7 @@ SYMBOLS = {
     "b200mf_cell_loop_range_dot": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),
     "b200mf_copy_constrained_values_dot": (C.c_int, [vp, vp, vp, vp, vp]),
     "b200mf_debug_resolve_hanging_nodes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint16, C.c_int, vp]),
+    "b200mf_vmult_host_batch": (C.c_int, [vp, C.POINTER(Operator), C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "b200mf_brick_probe": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "b200mf_vmult_prepare": (C.c_int, [vp, C.POINTER(Operator), vp, vp]),
     "b200mf_vmult_range": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),

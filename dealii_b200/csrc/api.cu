@@ -671,6 +671,12 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);
   for (void *w : s->d_stage) cudaFree(w);
+  for (int i = 0; i < 2; ++i) { cudaFree(s->d_pipe_in[i]); cudaFree(s->d_pipe_out[i]); }
+  for (int i = 0; i < 3; ++i) {
+    if (s->pipe_stream[i]) cudaStreamDestroy(s->pipe_stream[i]);
+    for (int j = 0; j < 2; ++j)
+      if (s->pipe_event[i][j]) cudaEventDestroy(s->pipe_event[i][j]);
+  }
   delete h;
   return B200MF_OK;
 }
@@ -827,6 +833,50 @@ int b200mf_vmult_host(const b200mf_setup *h, const b200mf_operator *op, void *ds
   B200MF_CUDA_CHECK(cudaMemcpyAsync(dst_host, s.d_stage[1], s.n_owned * number_size(s.number),
                                     cudaMemcpyDeviceToHost, 0));
   B200MF_CUDA_CHECK(cudaStreamSynchronize(0));
+  return B200MF_OK;
+}
+
+int b200mf_vmult_host_batch(const b200mf_setup *h, const b200mf_operator *op, int n_vectors,
+                            void *const *dst_host, const void *const *src_host) {
+  B200MF_REQUIRE(h && op && n_vectors >= 0 && (n_vectors == 0 || (dst_host && src_host)), "null argument");
+  Setup &s = const_cast<Setup &>(h->impl);
+  const size_t bytes = (s.n_owned + s.n_ghost) * number_size(s.number);
+  const size_t owned_bytes = s.n_owned * number_size(s.number);
+  for (int i = 0; i < 2; ++i) {
+    if (!s.d_pipe_in[i]) B200MF_CUDA_CHECK(cudaMalloc(&s.d_pipe_in[i], std::max<size_t>(bytes, 1)));
+    if (!s.d_pipe_out[i]) B200MF_CUDA_CHECK(cudaMalloc(&s.d_pipe_out[i], std::max<size_t>(bytes, 1)));
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (!s.pipe_stream[i]) B200MF_CUDA_CHECK(cudaStreamCreateWithFlags(&s.pipe_stream[i], cudaStreamNonBlocking));
+    for (int j = 0; j < 2; ++j)
+      if (!s.pipe_event[i][j])
+        B200MF_CUDA_CHECK(cudaEventCreateWithFlags(&s.pipe_event[i][j], cudaEventDisableTiming));
+  }
+  cudaStream_t s_in = s.pipe_stream[0], s_op = s.pipe_stream[1], s_out = s.pipe_stream[2];
+  if (s.n_ghost) { // ghost sections of the inputs are read by the cell loop: zero once
+    for (int i = 0; i < 2; ++i)
+      B200MF_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(s.d_pipe_in[i]) + owned_bytes, 0, bytes - owned_bytes, s_in));
+  }
+  // three-stage pipeline over two slots: upload of vector k+1 and download of vector k-1 (both
+  // directions of the link at once) run while vector k is multiplied
+  for (int k = 0; k < n_vectors; ++k) {
+    const int slot = k & 1;
+    B200MF_REQUIRE(dst_host[k] && src_host[k], "null vector in batch");
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_in, s.pipe_event[1][slot], 0));   // input slot consumed (k-2)
+    B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_pipe_in[slot], src_host[k], owned_bytes, cudaMemcpyHostToDevice, s_in));
+    B200MF_CUDA_CHECK(cudaEventRecord(s.pipe_event[0][slot], s_in));
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_op, s.pipe_event[0][slot], 0));   // input arrived
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_op, s.pipe_event[2][slot], 0));   // output slot downloaded (k-2)
+    int rc = vmult_impl(s, *op, s.d_pipe_out[slot], s.d_pipe_in[slot], s_op, nullptr);
+    if (rc != B200MF_OK) return rc;
+    B200MF_CUDA_CHECK(cudaEventRecord(s.pipe_event[1][slot], s_op));
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_out, s.pipe_event[1][slot], 0));
+    B200MF_CUDA_CHECK(cudaMemcpyAsync(dst_host[k], s.d_pipe_out[slot], owned_bytes, cudaMemcpyDeviceToHost, s_out));
+    B200MF_CUDA_CHECK(cudaEventRecord(s.pipe_event[2][slot], s_out));
+  }
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(s_out));
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(s_op));
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(s_in));
   return B200MF_OK;
 }
 

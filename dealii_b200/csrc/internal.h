@@ -141,6 +141,10 @@ struct Setup {
   uint64_t work_elems = 0;
   // staging buffers for the *_host entry points
   void *d_stage[2] = {nullptr, nullptr};
+  // pipeline of b200mf_vmult_host_batch: two input and two output staging vectors, three streams
+  void *d_pipe_in[2] = {nullptr, nullptr}, *d_pipe_out[2] = {nullptr, nullptr};
+  cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr}; // h2d, compute, d2h
+  cudaEvent_t pipe_event[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 size_t number_size(int number);

@@ -236,6 +236,13 @@ class MatrixFreeOperator:
         L.check(self.mf._lib.b200mf_vmult_host(self.mf._h, C.byref(self.op), _npptr(dst_host),
                                                _npptr(src_host)))
 
+    def vmult_host_batch(self, dst_hosts, src_hosts):
+        """dst_hosts[k] = A src_hosts[k] for lists of (pinned) host numpy arrays, copies pipelined."""
+        n = len(src_hosts)
+        dp = (C.c_void_p * n)(*[d.ctypes.data for d in dst_hosts])
+        sp = (C.c_void_p * n)(*[s.ctypes.data for s in src_hosts])
+        L.check(self.mf._lib.b200mf_vmult_host_batch(self.mf._h, C.byref(self.op), n, dp, sp))
+
     def compute_diagonal(self):
         """examples/step-64/step-64.cc:339-368: diagonal by MatrixFreeTools::compute_diagonal,
         then inverted in place; returns the DiagonalMatrix."""

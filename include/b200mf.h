@@ -192,6 +192,13 @@ int b200mf_compute_diagonal(const b200mf_setup *s, const b200mf_operator *op, vo
 int b200mf_vmult_host(const b200mf_setup *s, const b200mf_operator *op, void *dst_host,
                       const void *src_host);
 
+/* n_vectors independent vmults dst_host[k] = A src_host[k] on HOST vectors (n_owned elements each,
+ * page-locked for the copies to overlap), pipelined over two device slots: the upload of vector
+ * k+1 and the download of vector k-1 use both directions of the host link while vector k is
+ * multiplied.  Returns after the last result has arrived.                                      */
+int b200mf_vmult_host_batch(const b200mf_setup *s, const b200mf_operator *op, int n_vectors,
+                            void *const *dst_host, const void *const *src_host);
+
 /* ------------------------------------------------------------------------------------
  * Vector kernels: LinearAlgebra::distributed::Vector<Number, MemorySpace::Default>
  * BLAS-1 (lac/vector_operations_internal.h:2140-2660).  n counts elements of `number`.

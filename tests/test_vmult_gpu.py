@@ -182,3 +182,14 @@ def test_linearity_and_symmetry_large():
     one = torch.ones_like(u)
     op.vmult(Au, one)
     assert Au.abs().max().item() < 1e-11 * scale
+
+
+def test_vmult_host_batch_matches_single_calls():
+    """b200mf_vmult_host_batch: pipelined host-to-host vmults of several vectors == one by one."""
+    om, oracle, mf, op = make_pair(3, 3, 2, "f64", mass=2.0)
+    rng = np.random.default_rng(21)
+    srcs = [torch.from_numpy(rng.random(om.n_dofs)).pin_memory() for _ in range(5)]
+    dsts = [torch.empty(om.n_dofs, dtype=torch.float64).pin_memory() for _ in range(5)]
+    op.vmult_host_batch([d.numpy() for d in dsts], [s.numpy() for s in srcs])
+    for s, d in zip(srcs, dsts):
+        assert rel_err(d.numpy(), oracle.vmult(s.numpy())) < 1e-12
