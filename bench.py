@@ -355,7 +355,7 @@ def run_engine(args):
         h_src2 = torch.empty(n_dofs, dtype=tdt).pin_memory()
         h_dst2 = torch.empty(n_dofs, dtype=tdt).pin_memory()
         h_src2.copy_(h_src)
-        nb = 10
+        nb = 16
         srcs = [(h_src if k % 2 == 0 else h_src2).numpy() for k in range(nb)]
         dsts = [(h_dst if k % 2 == 0 else h_dst2).numpy() for k in range(nb)]
         op.vmult_host_batch(dsts[:2], srcs[:2])
