@@ -41,6 +41,12 @@ class SetupInfo(C.Structure):
                 ("n_bricks", u64), ("cells_per_brick", u64)]
 
 
+class BulkInfo(C.Structure):
+    _fields_ = [("n_bricks", u64), ("n_patterns", u64), ("n_own", u64), ("n_first_scalar", u64),
+                ("n_later", u64), ("n_zero", u64), ("n_general_cells", u64), ("n_boundary_bricks", u64),
+                ("usable", C.c_int)]
+
+
 class Operator(C.Structure):
     _fields_ = [("grad_coefficient", vp), ("mass_coefficient", vp),
                 ("grad_constant", C.c_double), ("mass_constant", C.c_double)]
@@ -115,6 +121,9 @@ SYMBOLS = {
     "b200mf_debug_resolve_hanging_nodes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint16, C.c_int, vp]),
     "b200mf_vmult_host_batch": (C.c_int, [vp, C.POINTER(Operator), C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "b200mf_brick_probe": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+    "b200mf_bulk_probe": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(BulkInfo)]),
+    "b200mf_setup_enable_bulk": (C.c_int, [vp, C.c_int]),
+    "b200mf_setup_get_bulk_info": (C.c_int, [vp, C.POINTER(BulkInfo)]),
     "b200mf_vmult_prepare": (C.c_int, [vp, C.POINTER(Operator), vp, vp]),
     "b200mf_vmult_range": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),
     "b200mf_cg_init": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, u64, vp, vp]),

@@ -37,6 +37,27 @@ DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 
+#define DECL_N(N)                                                                           \
+  int launch_bulk_n##N(const Setup &, const b200mf_operator &, void *, const void *, cudaStream_t, double *);
+DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
+#undef DECL_N
+
+int launch_bulk(const Setup &s, const b200mf_operator &op, void *dst, const void *src, cudaStream_t st,
+                double *dot) {
+  switch (s.n) {
+    case 2: return launch_bulk_n2(s, op, dst, src, st, dot);
+    case 3: return launch_bulk_n3(s, op, dst, src, st, dot);
+    case 4: return launch_bulk_n4(s, op, dst, src, st, dot);
+    case 5: return launch_bulk_n5(s, op, dst, src, st, dot);
+    case 6: return launch_bulk_n6(s, op, dst, src, st, dot);
+    case 7: return launch_bulk_n7(s, op, dst, src, st, dot);
+    case 8: return launch_bulk_n8(s, op, dst, src, st, dot);
+    case 9: return launch_bulk_n9(s, op, dst, src, st, dot);
+  }
+  set_error("unsupported degree %d", s.degree);
+  return B200MF_ERR_UNSUPPORTED;
+}
+
 #define DECL_N(N) int debug_resolve_n##N(int, int, unsigned, int, double *);
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
@@ -461,8 +482,44 @@ int vmult_prepare_impl(const Setup &s, const b200mf_operator &op, void *dst, cud
   return B200MF_OK;
 }
 
+// bulk brick path usable for this call?  (bulk copies need 16-byte aligned vectors)
+bool bulk_enabled(const Setup &s, const b200mf_operator &op, const void *dst, const void *src) {
+  static const bool legacy = std::getenv("B200MF_KERNEL") != nullptr && std::string(std::getenv("B200MF_KERNEL")) == "brick";
+  return s.bulk.ready && s.bulk.enabled && !legacy && bricks_enabled(s, op) && dst != src &&
+         (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+}
+
+// vmult through the bulk brick kernel: zero what no brick stores, cells outside bricks with the
+// per-cell kernels (atomics), then every brick in one launch
+int vmult_bulk_impl(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                    cudaStream_t st, double *dot_accum) {
+  const Setup::Bulk &B = s.bulk;
+  const size_t ns = number_size(s.number);
+  if (s.n_ghost)
+    B200MF_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(dst) + s.n_owned * ns, 0, s.n_ghost * ns, st));
+  if (B.n_zero) {
+    const unsigned blocks = (unsigned)((B.n_zero + 255) / 256);
+    if (s.number == B200MF_F64)
+      set_constrained_kernel<double><<<blocks, 256, 0, st>>>((double *)dst, 0.0, B.d_zero, B.n_zero);
+    else
+      set_constrained_kernel<float><<<blocks, 256, 0, st>>>((float *)dst, 0.0f, B.d_zero, B.n_zero);
+    count_launch();
+    B200MF_CUDA_CHECK(cudaGetLastError());
+  }
+  for (const auto &r : B.general_ranges) {
+    int rc = launch_cells(s, op, dst, src, r.first, r.second, st, false, dot_accum);
+    if (rc != B200MF_OK) return rc;
+  }
+  return launch_bulk(s, op, dst, src, st, dot_accum);
+}
+
 int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                cudaStream_t st, double *dot_accum) {
+  if (bulk_enabled(s, op, dst, src)) {
+    int rc = vmult_bulk_impl(s, op, dst, src, st, dot_accum);
+    if (rc != B200MF_OK) return rc;
+    return copy_constrained_impl(s, dst, src, st, dot_accum);
+  }
   int rc0 = vmult_prepare_impl(s, op, dst, st);
   if (rc0 != B200MF_OK) return rc0;
   int rc = launch_cell_loop(s, op, dst, src, 0, s.n_cells, st, dot_accum, true);
@@ -668,6 +725,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
   cudaFree(s->d_diag_tables);
   cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map); cudaFree(s->d_zero_list);
+  free_bulk(*s);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);
   for (void *w : s->d_stage) cudaFree(w);
@@ -770,6 +828,44 @@ int b200mf_brick_probe(const b200mf_setup_desc *d, uint64_t *n_bricks, uint64_t 
   *n_bricks = s.n_bricks;
   *cells_per_brick = (uint64_t)s.brick_b * s.brick_b * s.brick_b;
   return rc;
+}
+
+int b200mf_bulk_probe(const b200mf_setup_desc *d, b200mf_bulk_info *info) {
+  B200MF_REQUIRE(d && info, "null argument");
+  B200MF_REQUIRE(d->dim == 3 && d->degree >= 1 && d->degree <= 8 && d->local_to_global, "bad descriptor");
+  std::memset(info, 0, sizeof(*info));
+  Setup s;
+  s.dim = d->dim; s.degree = d->degree; s.n = d->degree + 1; s.number = d->number;
+  s.n_cells = d->n_cells; s.n_owned = d->n_owned_dofs; s.n_ghost = d->n_ghost_dofs;
+  s.cell_kind = B200MF_CELLS_CARTESIAN; s.n_geom = 1;
+  if (d->constraint_mask)
+    for (uint64_t c = 0; c < d->n_cells; ++c)
+      if (d->constraint_mask[c]) s.any_mask = true;
+  BulkStats st{};
+  uint64_t nc = 0;
+  int rc = build_bricks(*d, s, false, &nc, &st);
+  if (rc != B200MF_OK) return rc;
+  info->n_bricks = st.n_bricks; info->n_patterns = st.n_patterns; info->n_own = st.n_own;
+  info->n_first_scalar = st.n_first_scalar; info->n_later = st.n_later; info->n_zero = st.n_zero;
+  info->n_general_cells = st.n_general_cells; info->n_boundary_bricks = st.n_boundary_bricks;
+  info->usable = s.bulk.ready ? 1 : 0;
+  return B200MF_OK;
+}
+
+int b200mf_setup_enable_bulk(b200mf_setup *h, int enable) {
+  B200MF_REQUIRE(h, "null argument");
+  h->impl.bulk.enabled = enable != 0;
+  return h->impl.bulk.ready ? 1 : 0;
+}
+
+int b200mf_setup_get_bulk_info(const b200mf_setup *h, b200mf_bulk_info *info) {
+  B200MF_REQUIRE(h && info, "null argument");
+  const BulkStats &st = h->impl.bulk.stats;
+  info->n_bricks = st.n_bricks; info->n_patterns = st.n_patterns; info->n_own = st.n_own;
+  info->n_first_scalar = st.n_first_scalar; info->n_later = st.n_later; info->n_zero = st.n_zero;
+  info->n_general_cells = st.n_general_cells; info->n_boundary_bricks = st.n_boundary_bricks;
+  info->usable = h->impl.bulk.ready ? 1 : 0;
+  return B200MF_OK;
 }
 
 int b200mf_vmult_prepare(const b200mf_setup *h, const b200mf_operator *op, void *dst, void *stream) {

@@ -27,7 +27,8 @@ inline void morton_decode(unsigned c, int &x, int &y, int &z) {
 } // namespace
 
 // Fills s.brick_* ; returns B200MF_OK also when no brick was found.
-int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_complete_out) {
+int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_complete_out,
+                 BulkStats *bulk_stats) {
   constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, COMPLETE = 0x40000000u, UNSET = 0xffffffffu;
   s.n_bricks = 0;
   s.brick_runs.clear();
@@ -119,6 +120,10 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   if (!upload) { // host-only probe (b200mf_brick_probe): counts, no device arrays
     s.n_bricks = nb;
     s.brick_b = b;
+    if (bulk_stats) {
+      maps.resize(nb * L3);
+      return build_bulk(d, s, maps, nb, false, bulk_stats);
+    }
     return B200MF_OK;
   }
   if (nb == 0) return B200MF_OK;
@@ -153,7 +158,8 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   s.brick_b = b;
   s.device_bytes += nb * L3 * sizeof(uint32_t);
   s.index_bytes += nb * L3 * sizeof(uint32_t);
-  return B200MF_OK;
+  maps.resize(nb * L3);
+  return build_bulk(d, s, maps, nb, true, bulk_stats);
 }
 
 } // namespace b200mf

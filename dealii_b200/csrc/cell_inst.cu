@@ -6,6 +6,8 @@
 #include "cell_kernels.cuh"
 #include "cell_kernels_plane.cuh"
 #include "brick_kernel.cuh"
+#include "bulk_kernel.cuh"
+#include <mutex>
 
 #ifndef B200MF_N
 #error "compile with -DB200MF_N=<degree+1>"
@@ -200,6 +202,66 @@ int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, cons
   return B200MF_OK;
 }
 
+// bulk brick path: every brick of the setup in one persistent launch (vmult mode: dst is written,
+// not added to)
+template <int p, typename Number, bool DOT>
+int launch_bulk_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                    cudaStream_t stream, double *dot_accum) {
+  constexpr int b = brick_edge(p);
+  using Cfg = BulkCfg<p, b, Number>;
+  const Setup::Bulk &B = s.bulk;
+  if (B.L != Cfg::L || B.TP != Cfg::threads) {
+    set_error("bulk tables were built for another brick shape");
+    return B200MF_ERR_INVALID;
+  }
+  BulkKernelParams<p, Number> prm;
+  fill_brick_matrices<Number, p + 1>(s, op, prm.mat);
+  prm.desc = B.d_desc; prm.tx = B.d_tx; prm.tz = B.d_tz; prm.holes = B.d_holes;
+  prm.flags = B.d_flags; prm.ticket = B.d_ticket;
+  prm.src = static_cast<const Number *>(src);
+  prm.dst = static_cast<Number *>(dst);
+  prm.dot_accum = dot_accum;
+  prm.n_exec = B.n_exec;
+  prm.epoch = ++s.bulk.epoch;
+  prm.max_holes = (uint32_t)B.max_holes;
+  prm.boundary_begin = prm.boundary_end = 0;
+  prm.ghost_ready = nullptr;
+  prm.boundary_done = nullptr;
+  if (B.sync_ghost_ready != nullptr) {
+    prm.boundary_begin = (uint32_t)B.exec_boundary_begin;
+    prm.boundary_end = (uint32_t)B.exec_boundary_end;
+    prm.ghost_ready = B.sync_ghost_ready;
+    prm.boundary_done = B.sync_boundary_done;
+  }
+  auto kernel = bulk_brick_kernel<p, b, Number, DOT>;
+  // per-device launch configuration (dynamic shared memory opt-in, persistent grid size)
+  static std::mutex mtx;
+  static int grid_of_device[64] = {0};
+  int dev = 0;
+  B200MF_CUDA_CHECK(cudaGetDevice(&dev));
+  int grid;
+  {
+    std::lock_guard<std::mutex> lock(mtx);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (grid_of_device[dev] == 0) {
+      B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::smem_bytes));
+      int sms = 0, per_sm = 0;
+      B200MF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      B200MF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::threads,
+                                                                      Cfg::smem_bytes));
+      if (per_sm < 1) per_sm = 1;
+      grid_of_device[dev] = sms * per_sm;
+    }
+    grid = grid_of_device[dev];
+  }
+  if ((uint64_t)grid > B.n_exec) grid = (int)B.n_exec;
+  kernel<<<(unsigned)grid, Cfg::threads, Cfg::smem_bytes, stream>>>(prm);
+  count_launch();
+  B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
 } // namespace
 
 #define B200MF_CAT2(a, b) a##b
@@ -218,6 +280,16 @@ int B200MF_CAT(debug_resolve_n, B200MF_N)(int dim, int number, unsigned mask, in
                                 : debug_resolve_one<2, B200MF_N, float>(mask, transpose, values_host);
   return number == B200MF_F64 ? debug_resolve_one<3, B200MF_N, double>(mask, transpose, values_host)
                               : debug_resolve_one<3, B200MF_N, float>(mask, transpose, values_host);
+}
+
+int B200MF_CAT(launch_bulk_n, B200MF_N)(const Setup &s, const b200mf_operator &op, void *dst,
+                                        const void *src, cudaStream_t st, double *dot) {
+  constexpr int p = B200MF_N - 1;
+  if (s.number == B200MF_F64)
+    return dot ? launch_bulk_one<p, double, true>(s, op, dst, src, st, dot)
+               : launch_bulk_one<p, double, false>(s, op, dst, src, st, dot);
+  return dot ? launch_bulk_one<p, float, true>(s, op, dst, src, st, dot)
+             : launch_bulk_one<p, float, false>(s, op, dst, src, st, dot);
 }
 
 #if B200MF_N <= 9

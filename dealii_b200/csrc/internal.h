@@ -96,6 +96,11 @@ struct OperatorArgs {
   int has_mass;
 };
 
+struct BulkStatsData {
+  uint64_t n_bricks = 0, n_patterns = 0, n_own = 0, n_first_scalar = 0, n_later = 0, n_zero = 0,
+           n_general_cells = 0, n_boundary_bricks = 0;
+};
+
 struct Setup {
   int dim = 0, degree = 0, n = 0, number = 0;
   uint64_t n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0, n_cells_interior = 0;
@@ -134,6 +139,25 @@ struct Setup {
   std::vector<BrickRun> brick_runs;
   double geom0[4] = {0, 0, 0, 0}; // cartesian metric diagonal + det of the single-geometry mesh
 
+  // bulk brick path (bulk_kernel.cuh / bulk_setup.cpp): pattern tables + per-brick descriptors in
+  // execution order, first-toucher-stores write protocol
+  struct Bulk {
+    bool ready = false, enabled = true;
+    BulkStatsData stats;
+    uint32_t n_exec = 0, n_patterns = 0;
+    int L = 0, TP = 0, max_holes = 0;
+    uint64_t exec_boundary_begin = 0, exec_boundary_end = 0; // bricks touching ghost dofs
+    uint32_t *d_desc = nullptr, *d_tx = nullptr, *d_tz = nullptr, *d_holes = nullptr;
+    uint32_t *d_flags = nullptr, *d_ticket = nullptr, *d_zero = nullptr;
+    uint64_t n_zero = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> general_ranges; // cells no brick covers
+    uint32_t epoch = 0; // launch counter: flags hold the epoch of the launch that set them
+    // distributed vmult (comm.cu): boundary bricks wait for *sync_ghost_ready == epoch and count
+    // themselves into *sync_boundary_done; null = no synchronisation with a ghost exchange
+    uint32_t *sync_ghost_ready = nullptr, *sync_boundary_done = nullptr;
+  };
+  mutable Bulk bulk;
+
   // scratch for reductions / solver
   double *d_scratch = nullptr;
   double *h_pinned = nullptr;
@@ -166,9 +190,17 @@ int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const
 int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *diag,
                             cudaStream_t stream);
 
+// bulk_setup.cpp
+using BulkStats = BulkStatsData;
+int build_bulk(const b200mf_setup_desc &d, Setup &s, const std::vector<uint32_t> &maps, uint64_t nb,
+               bool upload, BulkStats *stats);
+void free_bulk(Setup &s);
+int launch_bulk(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                cudaStream_t stream, double *dot_accum);
+
 // brick_setup.cpp
 int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload = true,
-                 uint64_t *n_complete_out = nullptr);
+                 uint64_t *n_complete_out = nullptr, BulkStats *bulk_stats = nullptr);
 // kernels: the bricks [brick_begin, brick_begin + n_bricks) of the setup
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                   uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,

@@ -202,6 +202,16 @@ class MatrixFree:
         L.check(self._lib.b200mf_vmult_range(self._h, C.byref(op), _ptr(dst), _ptr(src), cell_begin,
                                              cell_end, C.c_void_p(dot_ptr) if dot_ptr else None, _stream()))
 
+    def enable_bulk(self, enable=True):
+        """A/B switch between the bulk brick tables and the per-node index maps (tests, bench);
+        returns whether the setup has bulk tables."""
+        return bool(self._lib.b200mf_setup_enable_bulk(self._h, int(bool(enable))))
+
+    def bulk_info(self):
+        info = L.BulkInfo()
+        L.check(self._lib.b200mf_setup_get_bulk_info(self._h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in L.BulkInfo._fields_}
+
     def copy_constrained_values(self, src, dst):
         L.check(self._lib.b200mf_copy_constrained_values(self._h, _ptr(dst), _ptr(src), _stream()))
 

@@ -142,6 +142,24 @@ int b200mf_debug_resolve_hanging_nodes(int dim, int degree, int number, uint16_t
 int b200mf_brick_probe(const b200mf_setup_desc *desc, uint64_t *n_bricks, uint64_t *cells_per_brick,
                        uint64_t *n_complete_dofs);
 
+/* HOST-only probe of the bulk brick tables the setup derives from the index lists (no device
+ * needed; dealii_b200/csrc/bulk_setup.cpp): the write protocol of vmult on brick meshes is "the first
+ * toucher of a dof stores it, later touchers add after the first toucher's flag"; this reports how
+ * the lattice nodes of all bricks split into own-range nodes (moved by bulk copies), first-toucher
+ * nodes outside an own range (scalar stores), later-toucher nodes (RED), how many distinct relative
+ * index patterns describe the bricks, and how many dofs have to be zeroed before a vmult because
+ * no brick stores them.  usable = 0 when the setup would fall back to the per-node index maps.  */
+typedef struct {
+  uint64_t n_bricks, n_patterns, n_own, n_first_scalar, n_later, n_zero, n_general_cells,
+      n_boundary_bricks;
+  int usable;
+} b200mf_bulk_info;
+int b200mf_bulk_probe(const b200mf_setup_desc *desc, b200mf_bulk_info *info);
+/* A/B switch (tests, bench): enable = 0 makes vmult use the per-node index maps + memset + atomics
+ * of the brick kernel instead of the bulk tables; returns whether bulk tables exist.             */
+int b200mf_setup_enable_bulk(b200mf_setup *s, int enable);
+int b200mf_setup_get_bulk_info(const b200mf_setup *s, b200mf_bulk_info *info);
+
 /* Quadrature point coordinates, the input of PMF::evaluate_coefficients functors
  * (portable_matrix_free.h:585, get_quadrature_point :417): writes
  * out[(cell*n_q_total + q)*dim + d] to a HOST array. */
