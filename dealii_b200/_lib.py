@@ -44,7 +44,8 @@ class SetupInfo(C.Structure):
 class BulkInfo(C.Structure):
     _fields_ = [("n_bricks", u64), ("n_patterns", u64), ("n_own", u64), ("n_first_scalar", u64),
                 ("n_later", u64), ("n_zero", u64), ("n_general_cells", u64), ("n_boundary_bricks", u64),
-                ("usable", C.c_int)]
+                ("usable", C.c_int), ("enabled", C.c_int),
+                ("tuned_ms_index_map", C.c_double), ("tuned_ms_bulk", C.c_double)]
 
 
 class Operator(C.Structure):

@@ -710,6 +710,48 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   cudaFree(d_qp);
   cudaFree(d_qw);
   s.device_bytes += s.geometry_bytes;
+  // "atomics or a colouring chosen by measurement" (north star; the reference offers graph
+  // colouring or atomics, portable_matrix_free.templates.h:1060-1185): when the setup has both the
+  // index-map brick path (memset + atomics on shared dofs) and the bulk brick path
+  // (first-toucher-stores, no memset), time a few vmults of each on scratch vectors and keep the
+  // faster one.  B200MF_BULK=0/1 forces the choice.
+  if (s.bulk.ready) {
+    const char *force = std::getenv("B200MF_BULK");
+    if (force != nullptr) {
+      s.bulk.enabled = std::atoi(force) != 0;
+    } else {
+      const size_t bytes = (s.n_owned + s.n_ghost) * number_size(s.number);
+      void *va = nullptr, *vb = nullptr;
+      if (cudaMalloc(&va, bytes) == cudaSuccess && cudaMalloc(&vb, bytes) == cudaSuccess) {
+        cudaMemset(va, 0, bytes);
+        b200mf_operator op{nullptr, nullptr, 1.0, 0.0};
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float ms[2] = {0.f, 0.f};
+        for (int mode = 0; mode < 2 && rc == B200MF_OK; ++mode) {
+          s.bulk.enabled = mode == 1;
+          for (int i = 0; i < 2 && rc == B200MF_OK; ++i) rc = vmult_impl(s, op, vb, va, nullptr, nullptr);
+          cudaEventRecord(e0, nullptr);
+          for (int i = 0; i < 4 && rc == B200MF_OK; ++i) rc = vmult_impl(s, op, vb, va, nullptr, nullptr);
+          cudaEventRecord(e1, nullptr);
+          cudaEventSynchronize(e1);
+          cudaEventElapsedTime(&ms[mode], e0, e1);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        s.bulk.enabled = rc == B200MF_OK && ms[1] < ms[0];
+        s.bulk.tuned_ms[0] = ms[0] / 4;
+        s.bulk.tuned_ms[1] = ms[1] / 4;
+        rc = B200MF_OK;
+      } else {
+        s.bulk.enabled = false;
+        (void)cudaGetLastError();
+      }
+      cudaFree(va);
+      cudaFree(vb);
+    }
+  }
   B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_scratch, 4096 * sizeof(double)));
   B200MF_CUDA_CHECK(cudaMallocHost((void **)&s.h_pinned, 64 * sizeof(double)));
   B200MF_CUDA_CHECK(cudaGetLastError());
@@ -865,6 +907,9 @@ int b200mf_setup_get_bulk_info(const b200mf_setup *h, b200mf_bulk_info *info) {
   info->n_first_scalar = st.n_first_scalar; info->n_later = st.n_later; info->n_zero = st.n_zero;
   info->n_general_cells = st.n_general_cells; info->n_boundary_bricks = st.n_boundary_bricks;
   info->usable = h->impl.bulk.ready ? 1 : 0;
+  info->enabled = h->impl.bulk.ready && h->impl.bulk.enabled ? 1 : 0;
+  info->tuned_ms_index_map = h->impl.bulk.tuned_ms[0];
+  info->tuned_ms_bulk = h->impl.bulk.tuned_ms[1];
   return B200MF_OK;
 }
 

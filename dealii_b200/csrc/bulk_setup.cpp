@@ -37,7 +37,7 @@ inline uint64_t hash_words(const uint32_t *w, size_t n, uint64_t h = 0x9e3779b97
 
 void free_bulk(Setup &s) {
   Setup::Bulk &B = s.bulk;
-  cudaFree(B.d_desc); cudaFree(B.d_tx); cudaFree(B.d_tz); cudaFree(B.d_holes);
+  cudaFree(B.d_desc); cudaFree(B.d_other); cudaFree(B.d_phdr); cudaFree(B.d_own_pos); cudaFree(B.d_other_pos);
   cudaFree(B.d_flags); cudaFree(B.d_ticket); cudaFree(B.d_zero);
   B = Setup::Bulk();
 }
@@ -119,7 +119,7 @@ int build_bulk(const b200mf_setup_desc &d, Setup &s, const std::vector<uint32_t>
   }
 
   // ---- per brick: own range, relative table, dependencies; patterns deduplicated by content
-  constexpr int kMaxDeps = 26, kMaxHoles = 1024, kDescWords = 48;
+  constexpr int kMaxDeps = 26, kMaxHoles = 1 << 20, kDescWords = 48;
   struct Pattern { std::vector<uint32_t> entries; std::vector<uint32_t> holes; };
   std::vector<Pattern> patterns;
   std::unordered_multimap<uint64_t, uint32_t> dict;
@@ -236,12 +236,15 @@ int build_bulk(const b200mf_setup_desc &d, Setup &s, const std::vector<uint32_t>
       const Pattern &P = patterns[pid];
       for (uint32_t i = 0; i < k.R; ++i) stored[k.lo + i] = 1;
       n_own_total += k.R - P.holes.size();
+      uint32_t later_here = 0;
       for (uint64_t e = 0; e < L3; ++e) {
         const uint32_t en = P.entries[e], sl = en >> 28;
         if (sl == 0 || sl == 15) continue;
         if (en & (1u << 27)) { stored[k.base[sl] + (en & 0x7ffffffu)] = 1; ++n_first_scalar; }
-        else ++n_later;
+        else ++later_here;
       }
+      D[46] = later_here;
+      n_later += later_here;
     }
   }
   if (failed) return B200MF_OK;
@@ -289,22 +292,42 @@ int build_bulk(const b200mf_setup_desc &d, Setup &s, const std::vector<uint32_t>
   B.n_zero = zero_list.size();
   if (!upload) { B.ready = true; return B200MF_OK; }
 
-  // ---- device tables: Tx[pattern][x][tid] (tid <-> (y, z)), Tz[pattern][z][tid] (tid <-> (x, y)),
-  // holes[pattern][1 + kMaxHoles]
-  const size_t tsz = (size_t)L * TP;
-  std::vector<uint32_t> tx(patterns.size() * tsz, 15u << 28), tz(patterns.size() * tsz, 15u << 28);
-  std::vector<uint32_t> holes(patterns.size() * (size_t)(1 + kMaxHoles), 0);
+  // ---- device tables per pattern (stride PS = L^3 rounded up to 16):
+  //   own_pos[PS]   uint16: lattice position of the i-th dof of the own range (0xffff: hole)
+  //   other[PS]     uint32: entries of the nodes outside the own range, later touchers first,
+  //                 then first touchers, then constrained nodes;  other_pos[PS] their positions
+  //   phdr[4]       n_other, n_later, n_first, 0
+  const size_t PS = (L3 + 15) / 16 * 16;
+  std::vector<uint16_t> own_pos(patterns.size() * PS, 0xffffu), other_pos(patterns.size() * PS, 0);
+  std::vector<uint32_t> other(patterns.size() * PS, 15u << 28), phdr(patterns.size() * 4, 0);
   for (size_t q = 0; q < patterns.size(); ++q) {
     const Pattern &P = patterns[q];
-    for (int Z = 0, e = 0; Z < L; ++Z)
-      for (int Y = 0; Y < L; ++Y)
-        for (int X = 0; X < L; ++X, ++e) {
-          tx[q * tsz + (size_t)X * TP + (Y + L * Z)] = P.entries[e];
-          tz[q * tsz + (size_t)Z * TP + (X + L * Y)] = P.entries[e];
-        }
-    holes[q * (1 + kMaxHoles)] = (uint32_t)P.holes.size();
-    std::copy(P.holes.begin(), P.holes.end(), holes.begin() + q * (1 + kMaxHoles) + 1);
+    std::vector<uint32_t> later, first, cons;
+    for (uint32_t e = 0; e < L3; ++e) {
+      const uint32_t en = P.entries[e], sl = en >> 28;
+      if (sl == 0) own_pos[q * PS + (en & 0x7ffffffu)] = (uint16_t)e;
+      else if (sl == 15) cons.push_back(e);
+      else if (en & (1u << 27)) first.push_back(e);
+      else later.push_back(e);
+    }
+    size_t k = 0;
+    for (const auto *lst : {&later, &first, &cons})
+      for (uint32_t e : *lst) {
+        other[q * PS + k] = P.entries[e];
+        other_pos[q * PS + k] = (uint16_t)e;
+        ++k;
+      }
+    phdr[q * 4 + 0] = (uint32_t)k;
+    phdr[q * 4 + 1] = (uint32_t)later.size();
+    phdr[q * 4 + 2] = (uint32_t)first.size();
   }
+  auto up16 = [&](uint16_t **dp, const std::vector<uint16_t> &v) -> int {
+    B200MF_CUDA_CHECK(cudaMalloc((void **)dp, std::max<size_t>(v.size(), 1) * sizeof(uint16_t)));
+    B200MF_CUDA_CHECK(cudaMemcpy(*dp, v.data(), v.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    s.device_bytes += v.size() * sizeof(uint16_t);
+    s.index_bytes += v.size() * sizeof(uint16_t);
+    return B200MF_OK;
+  };
   auto up = [&](uint32_t **dp, const std::vector<uint32_t> &v) -> int {
     B200MF_CUDA_CHECK(cudaMalloc((void **)dp, std::max<size_t>(v.size(), 1) * sizeof(uint32_t)));
     B200MF_CUDA_CHECK(cudaMemcpy(*dp, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -314,16 +337,16 @@ int build_bulk(const b200mf_setup_desc &d, Setup &s, const std::vector<uint32_t>
   };
   int rc;
   if ((rc = up(&B.d_desc, desc)) != B200MF_OK) return rc;
-  if ((rc = up(&B.d_tx, tx)) != B200MF_OK) return rc;
-  if ((rc = up(&B.d_tz, tz)) != B200MF_OK) return rc;
-  if ((rc = up(&B.d_holes, holes)) != B200MF_OK) return rc;
+  if ((rc = up(&B.d_other, other)) != B200MF_OK) return rc;
+  if ((rc = up(&B.d_phdr, phdr)) != B200MF_OK) return rc;
+  if ((rc = up16(&B.d_own_pos, own_pos)) != B200MF_OK) return rc;
+  if ((rc = up16(&B.d_other_pos, other_pos)) != B200MF_OK) return rc;
   if ((rc = up(&B.d_zero, zero_list)) != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaMalloc((void **)&B.d_flags, nb * sizeof(uint32_t)));
   B200MF_CUDA_CHECK(cudaMemset(B.d_flags, 0, nb * sizeof(uint32_t)));
   B200MF_CUDA_CHECK(cudaMalloc((void **)&B.d_ticket, 64));
   B200MF_CUDA_CHECK(cudaMemset(B.d_ticket, 0, 64));
   s.device_bytes += nb * sizeof(uint32_t) + 64;
-  B.max_holes = kMaxHoles;
   B.ready = true;
   return B200MF_OK;
 }

@@ -216,17 +216,18 @@ int launch_bulk_one(const Setup &s, const b200mf_operator &op, void *dst, const 
   }
   BulkKernelParams<p, Number> prm;
   fill_brick_matrices<Number, p + 1>(s, op, prm.mat);
-  prm.desc = B.d_desc; prm.tx = B.d_tx; prm.tz = B.d_tz; prm.holes = B.d_holes;
+  prm.desc = B.d_desc; prm.other = B.d_other; prm.phdr = B.d_phdr;
+  prm.own_pos = B.d_own_pos; prm.other_pos = B.d_other_pos;
   prm.flags = B.d_flags; prm.ticket = B.d_ticket;
   prm.src = static_cast<const Number *>(src);
   prm.dst = static_cast<Number *>(dst);
   prm.dot_accum = dot_accum;
   prm.n_exec = B.n_exec;
   prm.epoch = ++s.bulk.epoch;
-  prm.max_holes = (uint32_t)B.max_holes;
   prm.boundary_begin = prm.boundary_end = 0;
   prm.ghost_ready = nullptr;
   prm.boundary_done = nullptr;
+  prm.debug = std::getenv("B200MF_BULK_DEBUG") ? (uint32_t)std::atoi(std::getenv("B200MF_BULK_DEBUG")) : 0u;
   if (B.sync_ghost_ready != nullptr) {
     prm.boundary_begin = (uint32_t)B.exec_boundary_begin;
     prm.boundary_end = (uint32_t)B.exec_boundary_end;

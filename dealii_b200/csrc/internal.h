@@ -143,11 +143,13 @@ struct Setup {
   // execution order, first-toucher-stores write protocol
   struct Bulk {
     bool ready = false, enabled = true;
+    float tuned_ms[2] = {0.f, 0.f}; // setup-time measurement: index-map path, bulk path
     BulkStatsData stats;
     uint32_t n_exec = 0, n_patterns = 0;
-    int L = 0, TP = 0, max_holes = 0;
+    int L = 0, TP = 0;
     uint64_t exec_boundary_begin = 0, exec_boundary_end = 0; // bricks touching ghost dofs
-    uint32_t *d_desc = nullptr, *d_tx = nullptr, *d_tz = nullptr, *d_holes = nullptr;
+    uint32_t *d_desc = nullptr, *d_other = nullptr, *d_phdr = nullptr;
+    uint16_t *d_own_pos = nullptr, *d_other_pos = nullptr;
     uint32_t *d_flags = nullptr, *d_ticket = nullptr, *d_zero = nullptr;
     uint64_t n_zero = 0;
     std::vector<std::pair<uint64_t, uint64_t>> general_ranges; // cells no brick covers

@@ -153,10 +153,16 @@ typedef struct {
   uint64_t n_bricks, n_patterns, n_own, n_first_scalar, n_later, n_zero, n_general_cells,
       n_boundary_bricks;
   int usable;
+  /* b200mf_setup_get_bulk_info only: which path vmult uses, and the per-vmult times the setup
+   * measured for both (0 when the choice was forced with B200MF_BULK=0/1)                      */
+  int enabled;
+  double tuned_ms_index_map, tuned_ms_bulk;
 } b200mf_bulk_info;
 int b200mf_bulk_probe(const b200mf_setup_desc *desc, b200mf_bulk_info *info);
-/* A/B switch (tests, bench): enable = 0 makes vmult use the per-node index maps + memset + atomics
- * of the brick kernel instead of the bulk tables; returns whether bulk tables exist.             */
+/* The setup times both brick paths (index maps + memset + atomics vs bulk tables +
+ * first-toucher-stores) on scratch vectors and keeps the faster one ("atomics or a colouring chosen
+ * by measurement").  This switch overrides the choice (tests, A/B runs); returns whether bulk
+ * tables exist.                                                                                  */
 int b200mf_setup_enable_bulk(b200mf_setup *s, int enable);
 int b200mf_setup_get_bulk_info(const b200mf_setup *s, b200mf_bulk_info *info);
 

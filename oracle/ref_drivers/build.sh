@@ -1,0 +1,31 @@
+#!/bin/bash
+# Builds the drivers that link the reference library of oracle/build_ref.sh (TEST INFRASTRUCTURE:
+# parity checker and CPU baseline only) into oracle/_ref/bin/.  Plain g++ on the files of this
+# directory; the reference's own headers/library are used where oracle/build_ref.sh installed them.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="$HERE/../_ref/install"
+BIN="$HERE/../_ref/bin"
+if [ ! -f "$REF/lib/libdeal_II.so" ] || [ ! -d "$REF/include/deal.II" ]; then
+  echo "ref_drivers/build.sh: no reference install with headers at $REF (run oracle/build_ref.sh where /root/reference exists)" >&2
+  exit 0
+fi
+mkdir -p "$BIN"
+CXX=${CXX:-g++}
+FLAGS="-std=c++17 -O2 -fopenmp-simd -march=x86-64-v4 -mprefer-vector-width=512 -Wno-unused-parameter -Wno-deprecated-declarations"
+INC="-I$REF/include -I$REF/include/deal.II/bundled"
+LINK="-L$REF/lib -ldeal_II -Wl,-rpath,\$ORIGIN/../install/lib -rdynamic -ldl -lpthread"
+pids=()
+for deg in ${DEGREES:-1 2 3 4 5 6 7 8}; do
+  if [ ! -x "$BIN/ref_dump_q$deg" ] || [ "$HERE/ref_dump.cc" -nt "$BIN/ref_dump_q$deg" ]; then
+    ( $CXX $FLAGS -DREF_DEGREE=$deg $INC "$HERE/ref_dump.cc" -o "$BIN/ref_dump_q$deg" $LINK ) &
+    pids+=($!)
+  fi
+done
+if [ ! -x "$BIN/ref_bench" ] || [ "$HERE/ref_bench.cc" -nt "$BIN/ref_bench" ]; then
+  ( $CXX $FLAGS $INC "$HERE/ref_bench.cc" -o "$BIN/ref_bench" $LINK ) &
+  pids+=($!)
+fi
+rc=0
+for p in "${pids[@]:-}"; do [ -z "$p" ] || wait "$p" || rc=1; done
+exit $rc

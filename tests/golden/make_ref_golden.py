@@ -1,0 +1,79 @@
+"""Generates tests/golden/ref/*.npz by RUNNING THE REFERENCE ITSELF: oracle/_ref/bin/ref_dump_q<p>
+(oracle/ref_drivers/ref_dump.cc linked against the unmodified deal.II built by oracle/build_ref.sh).
+
+Every file holds, for one small configuration, the setup arrays Portable::MatrixFree built
+(local_to_global with hanging-node redirection, ConstraintKinds masks, ...) and the results the
+reference computed with them: dst of the CPU MatrixFree cell loop and of Portable::MatrixFree,
+compute_diagonal, SolverCG iteration counts.  The GPU parity tests (tests/test_reference_parity.py)
+feed the same arrays to the engine and compare PER ENTRY.
+
+    python tests/golden/make_ref_golden.py          # needs oracle/_ref (this container only)
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+OUT = os.path.join(ROOT, "tests", "golden", "ref")
+
+# name: (dim, degree, refinements, mesh, op, dirichlet, keep_jacobians)
+CASES = {
+    # configs[1]: 3D Laplace on the affine Cartesian hyper_cube, every degree
+    "c2_q1": (3, 1, 3, "cartesian", "laplace", 0, False),
+    "c2_q2": (3, 2, 3, "cartesian", "laplace", 0, False),
+    "c2_q3": (3, 3, 2, "cartesian", "laplace", 0, False),
+    "c2_q4": (3, 4, 2, "cartesian", "laplace", 0, False),
+    "c2_q5": (3, 5, 1, "cartesian", "laplace", 0, False),
+    "c2_q6": (3, 6, 1, "cartesian", "laplace", 0, False),
+    "c2_q7": (3, 7, 1, "cartesian", "laplace", 0, False),
+    "c2_q8": (3, 8, 1, "cartesian", "laplace", 0, False),
+    "c2_q4_dirichlet": (3, 4, 2, "cartesian", "laplace", 1, False),
+    # configs[2]: step-64 Helmholtz, variable coefficient, Q5 (and the shipped Q3), zero Dirichlet
+    "c3_q5_step64": (3, 5, 2, "cartesian", "helmholtz_var", 1, False),
+    "c3_q3_step64": (3, 3, 2, "cartesian", "helmholtz_var", 1, False),
+    "c3_q3_hanging": (3, 3, 2, "hanging", "helmholtz_var", 1, False),
+    "c3_q2_hanging_const": (3, 2, 2, "hanging", "helmholtz", 0, False),
+    # configs[3]: Q3 Poisson with one refinement ball (hanging nodes), zero Dirichlet
+    "c4_q3_ball": (3, 3, 3, "ball", "laplace", 1, False),
+    "c4_q1_ball": (3, 1, 3, "ball", "laplace", 1, False),
+    # configs[4]: deformed (full-Jacobian) cells
+    "c5_q2_deformed": (3, 2, 2, "deformed", "laplace", 0, True),
+    "c5_q4_deformed": (3, 4, 2, "deformed", "laplace", 0, False),
+    "c5_q3_deformed_helmholtz": (3, 3, 2, "deformed", "helmholtz_var", 1, False),
+    # 2D
+    "d2_q2_hanging": (2, 2, 3, "hanging", "helmholtz_var", 1, True),
+    "d2_q4_cartesian": (2, 4, 3, "cartesian", "laplace", 1, False),
+}
+
+
+def run_case(name, spec):
+    dim, degree, ref, mesh, op, dirichlet, keep_jac = spec
+    exe = os.path.join(BIN, f"ref_dump_q{degree}")
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.check_call([exe, str(dim), str(degree), str(ref), mesh, op, str(dirichlet), tmp])
+        man = json.load(open(os.path.join(tmp, "manifest.json")))
+        out = {}
+        for k, v in man.items():
+            if isinstance(v, dict):
+                if k in ("inv_jacobian", "JxW") and not keep_jac:
+                    continue
+                if k in ("q_points",) or (k == "coefficient" and op != "helmholtz_var"):
+                    continue
+                out[k] = np.fromfile(os.path.join(tmp, v["file"]), dtype=v["dtype"])
+                assert out[k].size == v["size"]
+            else:
+                out[k] = np.array(v)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, {k: (v.shape if v.ndim else v.item()) for k, v in out.items() if v.ndim == 0 or k in ("src",)})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        run_case(n, CASES[n])
