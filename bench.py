@@ -149,26 +149,78 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference
-def cpu_reference_sample(degree, refinements, steps, warmup, deformation=0.0):
-    """The reference's CPU MatrixFree path (C restatement oracle/mf_cpu.c) on every host core:
-    one independent single-rank instance per core on its own hyper_cube(refinements) -- the
-    only way the reference uses several cores without MPI/TBB (zero communication cost)."""
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_bench")
+
+
+def reference_available():
+    return os.path.exists(REF_BENCH) and os.path.exists(
+        os.path.join(ROOT, "oracle", "_ref", "install", "lib", "libdeal_II.so"))
+
+
+def cpu_reference_sample(degree, refinements, steps, warmup, deformation=0.0, mode="vmult"):
+    """The reference's own vectorised CPU MatrixFree path on every host core.
+
+    With oracle/_ref present (deal.II built from /root/reference by oracle/build_ref.sh): the
+    UNMODIFIED library through oracle/_ref/bin/ref_bench (operator of
+    tests/performance/timing_matrix_free_kokkos.cc:56-111), one pinned single-rank process per
+    core -- the image has no MPI/TBB, so this is how the reference uses several cores; zero
+    communication cost, i.e. an upper bound for "MatrixFree with MPI" on the same cores -- all
+    released together by a start file; kind = "reference".  Without it: the C restatement
+    oracle/mf_cpu.c, kind = "port"."""
+    cores = sorted(os.sched_getaffinity(0))
+    if reference_available() and deformation == 0.0:
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            start = os.path.join(tmp, "go")
+            procs = [subprocess.Popen(["taskset", "-c", str(c), REF_BENCH, str(degree), str(refinements),
+                                       str(steps), str(max(warmup, 1)), mode, start],
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                     for c in cores]
+            # every instance finishes its setup + warm-up, then polls for the start file
+            # the instances poll for the start file once their setup + warm-up is done: give the
+            # slowest setup a generous, size-scaled head start
+            setup_wait = {1: 0.5, 2: 0.5, 3: 1.0, 4: 2.0, 5: 6.0, 6: 25.0, 7: 240.0}.get(refinements, 30.0) * (2.0 if mode == "cg" else 1.0)
+            time.sleep(setup_wait)
+            open(start, "w").close()
+            outs = [p.communicate(timeout=900) for p in procs]
+        res = []
+        for p, (o, e) in zip(procs, outs):
+            if p.returncode != 0:
+                raise RuntimeError(f"ref_bench failed: {e[-400:]}")
+            res.append(json.loads(o.strip().splitlines()[-1]))
+        t = max(r["seconds"] for r in res)
+        n_dofs = res[0]["n_dofs"]
+        total = len(cores) * n_dofs
+        units = steps if mode == "vmult" else res[0]["iterations"]
+        return {"value": total * units / t / 1e9, "unit": UNIT if mode == "vmult" else "GDoF-iterations/s",
+                "cores": len(cores), "kind": "reference",
+                "sample": (f"deal.II 9.9.0-pre built from /root/reference (oracle/_ref), CPU MatrixFree "
+                           f"{'vmult' if mode == 'vmult' else 'SolverCG + Jacobi'} "
+                           f"(operator of tests/performance/timing_matrix_free_kokkos.cc:56-111, AVX-512 "
+                           f"VectorizedArray<double,{res[0]['vectorization_lanes']}>): {len(cores)} pinned "
+                           f"single-rank processes (no MPI/TBB in the image), each 3D Q{degree} hyper_cube "
+                           f"refine_global({refinements}) = {n_dofs} DoFs, {units} "
+                           f"{'vmults' if mode == 'vmult' else 'iterations'} after {max(warmup, 1)} warm-up, common "
+                           f"start, slowest instance's time; the full-size mesh (refine_global(7)) does not fit "
+                           f"the reference's host setup {len(cores)} times"),
+                "seconds": t, "dofs_per_step": total, "sample_refinements": refinements,
+                "per_core_mdofs": n_dofs * units / t / 1e6}
     import numpy as np
     import dealii_b200                       # host-side mesh generator only (no GPU work)
     from oracle.mf_cpu import MatrixFreeCPU, time_vmult_on_cores
-    cores = len(os.sched_getaffinity(0))
+    ncores = len(cores)
     mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements,
                                      deformation_amplitude=deformation)
-    ops = [MatrixFreeCPU(3, degree, mesh.l2g, mesh.cell_vertices, mesh.n_dofs) for _ in range(cores)]
-    srcs = [np.random.default_rng(42 + i).random(mesh.n_dofs) for i in range(cores)]
+    ops = [MatrixFreeCPU(3, degree, mesh.l2g, mesh.cell_vertices, mesh.n_dofs) for _ in range(ncores)]
+    srcs = [np.random.default_rng(42 + i).random(mesh.n_dofs) for i in range(ncores)]
     t = time_vmult_on_cores(ops, srcs, steps, warmup=max(warmup, 1))
-    total = cores * mesh.n_dofs
-    return {"value": total * steps / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"{cores} concurrent single-rank instances (1 per core) of oracle/mf_cpu.c, each "
+    total = ncores * mesh.n_dofs
+    return {"value": total * steps / t / 1e9, "unit": UNIT, "cores": ncores, "kind": "port",
+            "sample": (f"{ncores} concurrent single-rank instances (1 per core) of oracle/mf_cpu.c (C "
+                       f"restatement of matrix_free/evaluation_kernels.h:1835-1916; oracle/_ref absent), each "
                        f"3D Q{degree} hyper_cube refine_global({refinements}) = {mesh.n_dofs} DoFs, "
-                       f"{steps} vmults after {max(warmup, 1)} warm-up; reference unbuildable here "
-                       f"(cmake), port follows matrix_free/evaluation_kernels.h:1835-1916"),
-            "seconds": t, "dofs_per_step": total}
+                       f"{steps} vmults after {max(warmup, 1)} warm-up"),
+            "seconds": t, "dofs_per_step": total, "sample_refinements": refinements}
 
 
 def run_reference(args):
@@ -176,13 +228,17 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 20))
-    r = cpu_reference_sample(args.degree, args.cpu_refinements, steps, min(args.warmup, 3),
-                             args.deformation)
+    warm = max(min(args.warmup, 5), 1)
+    r = cpu_reference_sample(args.degree, args.cpu_refinements, steps, warm, args.deformation)
+    cfg = workload_config(args, r["dofs_per_step"], "host cores only")
+    cfg["sample"] = (f"bounded sample: refine_global({r['sample_refinements']}) per core instead of "
+                     f"refine_global({args.refinements}) per GPU (per-DoF CPU throughput out of cache does not "
+                     f"depend on the size)")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": steps, "warmup": max(min(args.warmup, 3), 1),
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": r["seconds"] / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, r["dofs_per_step"], "host cores only"),
+            "config": cfg,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -290,15 +346,21 @@ def run_engine(args):
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline: the cell-loop kernel alone (CUDA events on its stream)
-    # (the launch vmult makes: the cell loop over all local cells in "dst was zeroed" mode)
+    # ---- roofline: the cell-loop kernel alone (CUDA events on its stream).  The library says which
+    # brick path its setup-time measurement chose: the bulk brick kernel IS the vmult (one launch,
+    # no memset); the index-map brick kernel is the launch that follows vmult's memset.
+    bulk = mf.bulk_info()
     reps = max(args.steps, 10)
+    if bulk["enabled"] and world == 1:
+        run_kernel = lambda: mf.vmult(op.op, dst, src)
+    else:
+        run_kernel = lambda: mf.vmult_range(op.op, dst, src, 0, mesh.n_cells)
     for _ in range(3):
-        mf.vmult_range(op.op, dst, src, 0, mesh.n_cells)
+        run_kernel()
     torch.cuda.synchronize()
     e0.record()
     for _ in range(reps):
-        mf.vmult_range(op.op, dst, src, 0, mesh.n_cells)
+        run_kernel()
     e1.record()
     torch.cuda.synchronize()
     ms_kernel = e0.elapsed_time(e1) / reps
@@ -312,7 +374,12 @@ def run_engine(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                "kernel": kernel_name(args, int(mf.info.n_bricks)),
+                "kernel": (kernel_name(args, int(mf.info.n_bricks)).replace("brick_cartesian_kernel", "bulk_brick_kernel")
+                           if bulk["enabled"] else kernel_name(args, int(mf.info.n_bricks))),
+                "brick_path": {"chosen": "bulk tables + first-toucher-stores" if bulk["enabled"] else
+                               "index maps + memset + atomics", "chosen_by": "setup-time measurement",
+                               "ms_index_map": bulk["tuned_ms_index_map"], "ms_bulk": bulk["tuned_ms_bulk"],
+                               "patterns": bulk["n_patterns"]},
                 "cells_in_bricks": int(mf.info.n_bricks * mf.info.cells_per_brick),
                 "cells": int(mesh.n_cells),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_dof": bpd, "peak_source": peak_src,
