@@ -86,6 +86,15 @@ class PartitionView(C.Structure):
                 ("lattice_ids", C.POINTER(u64))]
 
 
+class AdaptiveDesc(C.Structure):
+    _fields_ = [("part", PartitionDesc), ("ball_radius", C.c_double), ("brick_friendly_order", C.c_int)]
+
+
+class AdaptiveView(C.Structure):
+    _fields_ = [("constraint_mask", u16p), ("active_cell_index", u32p), ("n_hanging_dofs", u64),
+                ("n_masked_cells", u64), ("dof_coords", f64p)]
+
+
 class MeshView(C.Structure):
     _fields_ = [("n_cells", u64), ("n_dofs", u64), ("n_boundary_dofs", u64),
                 ("dofs_per_cell", C.c_int), ("vertices_per_cell", C.c_int), ("dim", C.c_int),
@@ -115,6 +124,8 @@ SYMBOLS = {
                                        C.POINTER(SolverResult)]),
     "b200mf_mesh_create": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(vp)]),
     "b200mf_mesh_create_partitioned": (C.c_int, [C.POINTER(PartitionDesc), C.POINTER(vp)]),
+    "b200mf_mesh_create_adaptive": (C.c_int, [C.POINTER(AdaptiveDesc), C.POINTER(vp)]),
+    "b200mf_mesh_adaptive_view_get": (C.c_int, [vp, C.POINTER(AdaptiveView)]),
     "b200mf_mesh_partition_view_get": (C.c_int, [vp, C.POINTER(PartitionView)]),
     "b200mf_cell_loop_range": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp]),
     "b200mf_cell_loop_range_dot": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),

@@ -17,25 +17,12 @@
 
 #include "internal.h"
 
-struct b200mf_mesh {
-  b200mf_mesh_desc desc;
-  uint64_t n_cells = 0, n_dofs = 0;
-  int dofs_per_cell = 0;
-  std::vector<uint32_t> l2g;
-  std::vector<double> vertices;
-  std::vector<uint32_t> boundary;
-  // partitioned meshes (b200mf_mesh_create_partitioned)
-  bool partitioned = false;
-  uint64_t n_global_dofs = 0, n_global_cells = 0, first_owned = 0, n_owned = 0, n_ghost = 0,
-           n_cells_interior = 0;
-  std::vector<uint64_t> rank_offsets, ghost_global, lattice_ids;
-};
+#include "mesh_internal.h"
 
 namespace b200mf {
-namespace {
 
 // offsets in [0,p]^dim of the dofs of FE_Q(p) in hierarchical order
-std::vector<std::array<int, 3>> hierarchic_offsets(int dim, int p) {
+std::vector<std::array<int, 3>> mesh_hierarchic_offsets(int dim, int p) {
   std::vector<std::array<int, 3>> out;
   auto add = [&](int x, int y, int z) { out.push_back(std::array<int, 3>{{x, y, z}}); };
   if (dim == 2) {
@@ -58,6 +45,9 @@ std::vector<std::array<int, 3>> hierarchic_offsets(int dim, int p) {
   }
   return out;
 }
+
+namespace {
+inline std::vector<std::array<int, 3>> hierarchic_offsets(int dim, int p) { return mesh_hierarchic_offsets(dim, p); }
 
 inline void cell_coords(const b200mf_mesh_desc &d, uint64_t c, int N, int ijk[3]) {
   ijk[0] = ijk[1] = ijk[2] = 0;
@@ -192,6 +182,7 @@ int b200mf_setup_create_from_mesh(const b200mf_mesh *m, int number, b200mf_setup
   d.local_to_global = m->l2g.data(); d.geometry = B200MF_GEOMETRY_Q1_VERTICES;
   d.cell_vertices = m->vertices.data();
   d.constrained_dofs = m->boundary.data(); d.n_constrained_dofs = m->boundary.size();
+  if (!m->cell_mask.empty()) d.constraint_mask = m->cell_mask.data();
   return b200mf_setup_create(&d, out);
 }
 

@@ -102,6 +102,11 @@ void lagrange(const std::vector<long double> &nodes, long double x, int i, long 
 
 } // namespace
 
+void build_fe_q_support_points(int degree, std::vector<double> &points) {
+  const std::vector<long double> xn = gauss_lobatto_points(degree + 1);
+  points.assign(xn.begin(), xn.end());
+}
+
 void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
                            std::vector<double> &q_points, std::vector<double> &subface) {

@@ -81,6 +81,69 @@ class PartitionedHyperCubeMesh(HyperCubeMesh):
                             if want_lattice_ids else None)
 
 
+class AdaptiveHyperCubeMesh(PartitionedHyperCubeMesh):
+    """This rank's cube of the partitioned mesh with one ball of refined cells per cube: hanging
+    nodes, ConstraintKinds masks, redirected index lists (b200mf_mesh_create_adaptive)."""
+
+    def __init__(self, dim, degree, refinements, n_ranks=1, rank=0, coarse=(1, 1, 1), ball_radius=0.3,
+                 dirichlet_boundary=False, mark_constrained_l2g=False, brick_friendly_order=True,
+                 want_coords=False):
+        lib = L.load()
+        a = L.AdaptiveDesc()
+        d = a.part
+        m = d.mesh
+        m.dim, m.degree = dim, degree
+        m.cells_per_direction, m.cell_order = 2 ** refinements, L.MESH_MORTON
+        m.left, m.right = 0.0, 1.0
+        m.deformation, m.deformation_amplitude = L.DEFORM_NONE, 0.0
+        m.dirichlet_boundary = int(dirichlet_boundary)
+        m.mark_constrained_l2g = int(mark_constrained_l2g)
+        for k in range(3):
+            d.coarse[k] = coarse[k] if k < len(coarse) else 1
+        d.n_ranks, d.rank = n_ranks, rank
+        d.ghost_mode = L.GHOSTS_TOUCHED
+        d.want_lattice_ids = int(want_coords)
+        a.ball_radius, a.brick_friendly_order = ball_radius, int(brick_friendly_order)
+        self._h = C.c_void_p()
+        L.check(lib.b200mf_mesh_create_adaptive(C.byref(a), C.byref(self._h)))
+        v = L.MeshView()
+        L.check(lib.b200mf_mesh_view_get(self._h, C.byref(v)))
+        pv = L.PartitionView()
+        L.check(lib.b200mf_mesh_partition_view_get(self._h, C.byref(pv)))
+        av = L.AdaptiveView()
+        L.check(lib.b200mf_mesh_adaptive_view_get(self._h, C.byref(av)))
+        self.dim, self.degree = dim, degree
+        self.n_cells, self.n_dofs = int(v.n_cells), int(v.n_dofs)
+        self.dofs_per_cell = int(v.dofs_per_cell)
+        self._view, self._aview = v, av
+        self.n_ranks, self.rank = n_ranks, rank
+        self.n_owned, self.n_ghost = int(pv.n_owned), int(pv.n_ghost)
+        self.n_global_dofs, self.n_global_cells = int(pv.n_global_dofs), int(pv.n_global_cells)
+        self.first_owned_global = int(pv.first_owned_global)
+        self.n_cells_interior = int(pv.n_cells_interior)
+        self.rank_offsets = np.ctypeslib.as_array(pv.rank_offsets, shape=(n_ranks + 1,)).copy()
+        self.ghost_global = (np.ctypeslib.as_array(pv.ghost_global, shape=(self.n_ghost,)).copy()
+                             if self.n_ghost else np.zeros(0, dtype=np.uint64))
+        self.lattice_ids = None
+        self.n_hanging_dofs, self.n_masked_cells = int(av.n_hanging_dofs), int(av.n_masked_cells)
+
+    @property
+    def constraint_mask(self):
+        return np.ctypeslib.as_array(self._aview.constraint_mask, shape=(self.n_cells,))
+
+    @property
+    def active_cell_index(self):
+        return np.ctypeslib.as_array(self._aview.active_cell_index, shape=(self.n_cells,))
+
+    @property
+    def constrained_dofs(self):
+        return self.boundary_dofs
+
+    @property
+    def dof_coords(self):
+        return np.ctypeslib.as_array(self._aview.dof_coords, shape=(self.n_owned + self.n_ghost, 3))
+
+
 class Partitioner:
     """Utilities::MPI::Partitioner: who sends what to whom.
 

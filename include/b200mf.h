@@ -385,6 +385,31 @@ typedef struct {
 } b200mf_partition_view;
 
 int b200mf_mesh_create_partitioned(const b200mf_partition_desc *desc, b200mf_mesh **out);
+
+/* The partitioned mesh with one level of adaptive refinement and hanging nodes (BASELINE
+ * configs[3]): n_ranks = number of coarse cubes, one cube per rank; every cell whose centre is
+ * closer than ball_radius (in cube edges) to the centre of its cube is refined once more, as
+ * tests/matrix_free/matrix_vector_03.cc refines.  Active cell order, DoF numbering
+ * (source/dofs/dof_handler_policy.cc:1676-1719: first touch, level by level), ConstraintKinds masks
+ * and the redirected index lists of Portable::MatrixFree (matrix_free/hanging_nodes_internal.h:
+ * 40-60, 520-880) are the reference's (bit-identical to deal.II on one rank, tests/test_adaptive_mesh.py);
+ * the constrained-dof list of the mesh view holds Dirichlet and hanging-node dofs.  ghost_mode must
+ * be B200MF_GHOSTS_TOUCHED.  brick_friendly_order = 1 emits the cells in an order that keeps whole
+ * unmasked b^3 blocks together (coarse blocks, refined blocks, other unmasked cells, masked cells,
+ * then the cells touching ghost dofs); active_cell_index maps back to the reference's order.   */
+typedef struct {
+  b200mf_partition_desc part;
+  double ball_radius;
+  int brick_friendly_order;
+} b200mf_adaptive_desc;
+typedef struct {
+  const uint16_t *constraint_mask;   /* [n_cells]                                            */
+  const uint32_t *active_cell_index; /* [n_cells] position in the reference's active cell order */
+  uint64_t n_hanging_dofs, n_masked_cells;
+  const double *dof_coords;          /* [n_owned + n_ghost][3] support points, if want_lattice_ids */
+} b200mf_adaptive_view;
+int b200mf_mesh_create_adaptive(const b200mf_adaptive_desc *desc, b200mf_mesh **out);
+int b200mf_mesh_adaptive_view_get(const b200mf_mesh *m, b200mf_adaptive_view *view);
 int b200mf_mesh_partition_view_get(const b200mf_mesh *m, b200mf_partition_view *view);
 int b200mf_mesh_view_get(const b200mf_mesh *m, b200mf_mesh_view *view);
 int b200mf_mesh_destroy(b200mf_mesh *m);
