@@ -28,12 +28,12 @@ size_t number_size(int number) { return number == B200MF_F64 ? 8 : 4; }
 
 #define DECL_N(N)                                                                             \
   int launch_cells_n##N(const Setup &, const b200mf_operator &, void *, const void *, uint64_t, \
-                        uint64_t, cudaStream_t, bool, double *);
+                        uint64_t, cudaStream_t, bool, double *, bool);
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 #define DECL_N(N)                                                                              \
   int launch_bricks_n##N(const Setup &, const b200mf_operator &, void *, const void *, uint64_t, \
-                         uint64_t, cudaStream_t, double *, bool);
+                         uint64_t, cudaStream_t, double *, bool, uint32_t);
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 
@@ -63,35 +63,49 @@ DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
-                  uint64_t bb, uint64_t nb, cudaStream_t st, double *dot, bool ow) {
+                  uint64_t bb, uint64_t nb, cudaStream_t st, double *dot, bool ow, uint32_t geom) {
   switch (s.n) {
-    case 2: return launch_bricks_n2(s, op, dst, src, bb, nb, st, dot, ow);
-    case 3: return launch_bricks_n3(s, op, dst, src, bb, nb, st, dot, ow);
-    case 4: return launch_bricks_n4(s, op, dst, src, bb, nb, st, dot, ow);
-    case 5: return launch_bricks_n5(s, op, dst, src, bb, nb, st, dot, ow);
-    case 6: return launch_bricks_n6(s, op, dst, src, bb, nb, st, dot, ow);
-    case 7: return launch_bricks_n7(s, op, dst, src, bb, nb, st, dot, ow);
-    case 8: return launch_bricks_n8(s, op, dst, src, bb, nb, st, dot, ow);
-    case 9: return launch_bricks_n9(s, op, dst, src, bb, nb, st, dot, ow);
+    case 2: return launch_bricks_n2(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 3: return launch_bricks_n3(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 4: return launch_bricks_n4(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 5: return launch_bricks_n5(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 6: return launch_bricks_n6(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 7: return launch_bricks_n7(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 8: return launch_bricks_n8(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 9: return launch_bricks_n9(s, op, dst, src, bb, nb, st, dot, ow, geom);
   }
   set_error("unsupported degree %d", s.degree);
   return B200MF_ERR_UNSUPPORTED;
 }
 
-static int launch_cells(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
-                        uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot) {
+static int launch_cells_part(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                             uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot, bool masked) {
+  if (e <= b) return B200MF_OK;
   switch (s.n) {
-    case 2: return launch_cells_n2(s, op, dst, src, b, e, st, diag, dot);
-    case 3: return launch_cells_n3(s, op, dst, src, b, e, st, diag, dot);
-    case 4: return launch_cells_n4(s, op, dst, src, b, e, st, diag, dot);
-    case 5: return launch_cells_n5(s, op, dst, src, b, e, st, diag, dot);
-    case 6: return launch_cells_n6(s, op, dst, src, b, e, st, diag, dot);
-    case 7: return launch_cells_n7(s, op, dst, src, b, e, st, diag, dot);
-    case 8: return launch_cells_n8(s, op, dst, src, b, e, st, diag, dot);
-    case 9: return launch_cells_n9(s, op, dst, src, b, e, st, diag, dot);
+    case 2: return launch_cells_n2(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 3: return launch_cells_n3(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 4: return launch_cells_n4(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 5: return launch_cells_n5(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 6: return launch_cells_n6(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 7: return launch_cells_n7(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 8: return launch_cells_n8(s, op, dst, src, b, e, st, diag, dot, masked);
+    case 9: return launch_cells_n9(s, op, dst, src, b, e, st, diag, dot, masked);
   }
   set_error("unsupported degree %d", s.degree);
   return B200MF_ERR_UNSUPPORTED;
+}
+
+// kernel selection per cell range: only the cells inside [masked_begin, masked_end) may carry a
+// hanging-node mask and need the kernel that resolves them
+static int launch_cells(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
+                        uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot) {
+  if (!s.any_mask) return launch_cells_part(s, op, dst, src, b, e, st, diag, dot, false);
+  const uint64_t mb = std::min(std::max(b, s.masked_begin), e), me = std::max(std::min(e, s.masked_end), mb);
+  int rc = launch_cells_part(s, op, dst, src, b, mb, st, diag, dot, false);
+  if (rc != B200MF_OK) return rc;
+  rc = launch_cells_part(s, op, dst, src, mb, me, st, diag, dot, true);
+  if (rc != B200MF_OK) return rc;
+  return launch_cells_part(s, op, dst, src, me, e, st, diag, dot, false);
 }
 
 static bool bricks_enabled(const Setup &s, const b200mf_operator &op) {
@@ -136,7 +150,7 @@ int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const
       if (rc != B200MF_OK) return rc;
     }
     int rc = launch_bricks(s, op, dst, src, run.first_brick + (rb - run.cell_begin) / W, (re - rb) / W,
-                           stream, dot_accum, dst_zeroed);
+                           stream, dot_accum, dst_zeroed, run.geom);
     if (rc != B200MF_OK) return rc;
     pos = re;
   }
@@ -600,8 +614,14 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     s.index_bytes += (real + pad) * sizeof(uint32_t);
   }
   if (d->constraint_mask) {
+    s.masked_begin = d->n_cells;
+    s.masked_end = 0;
     for (uint64_t c = 0; c < d->n_cells; ++c)
-      if (d->constraint_mask[c]) { s.any_mask = true; break; }
+      if (d->constraint_mask[c]) {
+        s.any_mask = true;
+        s.masked_begin = std::min(s.masked_begin, c);
+        s.masked_end = c + 1;
+      }
     if (s.any_mask)
       TRY(dev_alloc_copy<uint16_t>(&s.d_mask, d->constraint_mask, d->n_cells, s, &s.index_bytes));
   }
@@ -666,9 +686,13 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
       else                        TRY(upload_converted<float>(&s.d_geom_table, table, s, &s.geometry_bytes));
       if (s.n_geom > 1)
         TRY(dev_alloc_copy<uint32_t>(&s.d_geom_id, geom_id.data(), geom_id.size(), s, &s.geometry_bytes));
-      if (s.cell_kind == B200MF_CELLS_CARTESIAN && s.n_geom == 1 && s.dim == 3) {
+      if (s.cell_kind == B200MF_CELLS_CARTESIAN && s.n_geom >= 1 && s.n_geom <= 64 && s.dim == 3) {
         for (int i = 0; i < 4; ++i) s.geom0[i] = table[i];
+        s.h_geom_table = table;
+        if (s.n_geom > 1) s.h_geom_id = geom_id;
         TRY(build_bricks(*d, s));
+        s.h_geom_id.clear();
+        s.h_geom_id.shrink_to_fit();
       }
     }
     // keep the vertices for quadrature point queries while they are small

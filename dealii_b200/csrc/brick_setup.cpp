@@ -32,7 +32,11 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, COMPLETE = 0x40000000u, UNSET = 0xffffffffu;
   s.n_bricks = 0;
   s.brick_runs.clear();
-  if (s.dim != 3 || s.cell_kind != B200MF_CELLS_CARTESIAN || s.any_mask || s.n_geom != 1) return B200MF_OK;
+  // a window qualifies when its cells carry no hanging-node mask and share one cell shape
+  if (s.dim != 3 || s.cell_kind != B200MF_CELLS_CARTESIAN || s.n_geom < 1 || s.n_geom > 64) return B200MF_OK;
+  const uint16_t *cmask = s.any_mask ? d.constraint_mask : nullptr;
+  const uint32_t *gid = (s.n_geom > 1 && s.h_geom_id.size() == s.n_cells) ? s.h_geom_id.data() : nullptr;
+  if (s.n_geom > 1 && gid == nullptr) return B200MF_OK;
   const uint64_t n_total = s.n_owned + s.n_ghost;
   if (n_total >= COMPLETE) return B200MF_OK;
   const int p = s.degree, n = s.n, b = brick_edge(s.degree);
@@ -75,6 +79,10 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
     uint32_t *lat = maps.data() + (uint64_t)w * L3;
     std::fill(lat, lat + L3, UNSET);
     bool good = true;
+    if (cmask)
+      for (unsigned c = 0; c < W && good; ++c) good = cmask[(uint64_t)w * W + c] == 0;
+    if (gid)
+      for (unsigned c = 1; c < W && good; ++c) good = gid[(uint64_t)w * W + c] == gid[(uint64_t)w * W];
     for (unsigned c = 0; c < W && good; ++c) {
       const uint32_t *cl = l2g + ((uint64_t)w * W + c) * npc;
       const int ox = cx[c] * p, oy = cy[c] * p, oz = cz[c] * p;
@@ -105,10 +113,11 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   for (uint64_t w = 0; w < n_windows; ++w) {
     if (!ok[w]) continue;
     if (nb != w) std::memmove(maps.data() + nb * L3, maps.data() + w * L3, L3 * sizeof(uint32_t));
-    if (!s.brick_runs.empty() && s.brick_runs.back().cell_end == w * W)
+    const uint32_t g = gid ? gid[w * W] : 0u;
+    if (!s.brick_runs.empty() && s.brick_runs.back().cell_end == w * W && s.brick_runs.back().geom == g)
       s.brick_runs.back().cell_end = (w + 1) * W;
     else
-      s.brick_runs.push_back({w * W, (w + 1) * W, nb});
+      s.brick_runs.push_back({w * W, (w + 1) * W, nb, g});
     ++nb;
   }
   if (n_complete_out) {
@@ -159,6 +168,7 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   s.device_bytes += nb * L3 * sizeof(uint32_t);
   s.index_bytes += nb * L3 * sizeof(uint32_t);
   maps.resize(nb * L3);
+  if (s.n_geom != 1) return B200MF_OK; // the bulk kernel applies one cell shape per launch
   return build_bulk(d, s, maps, nb, true, bulk_stats);
 }
 

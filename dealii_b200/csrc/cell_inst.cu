@@ -20,12 +20,12 @@ namespace {
 template <int dim, int n, typename Number, int KIND>
 int launch_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream, bool diagonal,
-               double *dot_accum) {
+               double *dot_accum, bool masked) {
   using Cfg = BlockCfg<dim, n>;
   CellKernelParams<dim, n, Number, KIND> p;
   fill_shape_data<Number, n>(s, p.shape);
   p.l2g = s.d_l2g;
-  p.mask = s.any_mask ? s.d_mask : nullptr;
+  p.mask = (s.any_mask && masked) ? s.d_mask : nullptr;
   p.geom_id = s.d_geom_id;
   p.geom_table = static_cast<const Number *>(s.d_geom_table);
   p.metric = static_cast<const Number *>(s.d_metric);
@@ -69,13 +69,19 @@ int launch_one(const Setup &s, const b200mf_operator &op, void *dst, const void 
       using PCfg = PlaneCfg<n, Number>;
       auto kernel = dot_accum != nullptr ? cell_loop_plane_kernel<n, Number, KIND, true>
                                          : cell_loop_plane_kernel<n, Number, KIND, false>;
-      static int resident_ctas_v[2] = {0, 0}; // persistent grid: SMs x resident CTAs per SM
-      int &resident_ctas = resident_ctas_v[dot_accum != nullptr ? 1 : 0];
+      // persistent grid: SMs x resident CTAs per SM, cached per device (the dynamic shared memory
+      // opt-in and the occupancy are per-device properties)
+      static std::mutex plane_mtx;
+      static int resident_ctas_v[64][2] = {};
+      int dev = 0;
+      B200MF_CUDA_CHECK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64) dev = 0;
+      std::lock_guard<std::mutex> plane_lock(plane_mtx);
+      int &resident_ctas = resident_ctas_v[dev][dot_accum != nullptr ? 1 : 0];
       if (resident_ctas == 0) {
         B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)PCfg::smem_bytes));
-        int dev = 0, sms = 0, per_sm = 0;
-        B200MF_CUDA_CHECK(cudaGetDevice(&dev));
+        int sms = 0, per_sm = 0;
         B200MF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         B200MF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PCfg::threads,
                                                                         PCfg::smem_bytes));
@@ -116,26 +122,26 @@ int launch_one(const Setup &s, const b200mf_operator &op, void *dst, const void 
 
 template <int dim, int n, typename Number>
 int launch_kind(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
-                uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot) {
+                uint64_t b, uint64_t e, cudaStream_t st, bool diag, double *dot, bool masked) {
   switch (s.cell_kind) {
     case B200MF_CELLS_CARTESIAN:
-      return launch_one<dim, n, Number, B200MF_CELLS_CARTESIAN>(s, op, dst, src, b, e, st, diag, dot);
+      return launch_one<dim, n, Number, B200MF_CELLS_CARTESIAN>(s, op, dst, src, b, e, st, diag, dot, masked);
     case B200MF_CELLS_AFFINE:
-      return launch_one<dim, n, Number, B200MF_CELLS_AFFINE>(s, op, dst, src, b, e, st, diag, dot);
+      return launch_one<dim, n, Number, B200MF_CELLS_AFFINE>(s, op, dst, src, b, e, st, diag, dot, masked);
     default:
-      return launch_one<dim, n, Number, B200MF_CELLS_GENERAL>(s, op, dst, src, b, e, st, diag, dot);
+      return launch_one<dim, n, Number, B200MF_CELLS_GENERAL>(s, op, dst, src, b, e, st, diag, dot, masked);
   }
 }
 
 template <int n>
 int launch_n(const Setup &s, const b200mf_operator &op, void *dst, const void *src, uint64_t b,
-             uint64_t e, cudaStream_t st, bool diag, double *dot) {
+             uint64_t e, cudaStream_t st, bool diag, double *dot, bool masked) {
   if (s.dim == 2) {
-    return s.number == B200MF_F64 ? launch_kind<2, n, double>(s, op, dst, src, b, e, st, diag, dot)
-                                  : launch_kind<2, n, float>(s, op, dst, src, b, e, st, diag, dot);
+    return s.number == B200MF_F64 ? launch_kind<2, n, double>(s, op, dst, src, b, e, st, diag, dot, masked)
+                                  : launch_kind<2, n, float>(s, op, dst, src, b, e, st, diag, dot, masked);
   }
-  return s.number == B200MF_F64 ? launch_kind<3, n, double>(s, op, dst, src, b, e, st, diag, dot)
-                                : launch_kind<3, n, float>(s, op, dst, src, b, e, st, diag, dot);
+  return s.number == B200MF_F64 ? launch_kind<3, n, double>(s, op, dst, src, b, e, st, diag, dot, masked)
+                                : launch_kind<3, n, float>(s, op, dst, src, b, e, st, diag, dot, masked);
 }
 
 // resolve_hanging_nodes of ONE cell, for the golden-vector test of the device code path
@@ -178,11 +184,11 @@ int debug_resolve_one(unsigned mask, int transpose, double *values_host) {
 template <int p, typename Number, bool DOT>
 int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                       uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
-                      bool overwrite) {
+                      bool overwrite, uint32_t geom) {
   constexpr int b = brick_edge(p);
   using Cfg = BrickCfg<p, b, Number>;
   BrickKernelParams<p, Number> prm;
-  fill_brick_matrices<Number, p + 1>(s, op, prm.mat);
+  fill_brick_matrices<Number, p + 1>(s, op, prm.mat, geom);
   prm.map = s.d_brick_map;
   prm.src = static_cast<const Number *>(src);
   prm.dst = static_cast<Number *>(dst);
@@ -190,12 +196,9 @@ int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, cons
   prm.brick_begin = brick_begin;
   prm.overwrite = overwrite ? 1 : 0;
   auto kernel = brick_cartesian_kernel<p, b, Number, DOT>;
-  static bool configured = false;
-  if (!configured) {
-    B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)Cfg::smem_bytes));
-    configured = true;
-  }
+  // (the attribute is per device: set it on every launch, it is a cheap driver call)
+  B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::smem_bytes));
   kernel<<<(unsigned)n_bricks, Cfg::threads, Cfg::smem_bytes, stream>>>(prm);
   count_launch();
   B200MF_CUDA_CHECK(cudaGetLastError());
@@ -270,8 +273,8 @@ int launch_bulk_one(const Setup &s, const b200mf_operator &op, void *dst, const 
 
 int B200MF_CAT(launch_cells_n, B200MF_N)(const Setup &s, const b200mf_operator &op, void *dst,
                                          const void *src, uint64_t b, uint64_t e,
-                                         cudaStream_t st, bool diag, double *dot) {
-  return launch_n<B200MF_N>(s, op, dst, src, b, e, st, diag, dot);
+                                         cudaStream_t st, bool diag, double *dot, bool masked) {
+  return launch_n<B200MF_N>(s, op, dst, src, b, e, st, diag, dot, masked);
 }
 
 int B200MF_CAT(debug_resolve_n, B200MF_N)(int dim, int number, unsigned mask, int transpose,
@@ -296,13 +299,13 @@ int B200MF_CAT(launch_bulk_n, B200MF_N)(const Setup &s, const b200mf_operator &o
 #if B200MF_N <= 9
 int B200MF_CAT(launch_bricks_n, B200MF_N)(const Setup &s, const b200mf_operator &op, void *dst,
                                           const void *src, uint64_t brick_begin, uint64_t n_bricks,
-                                          cudaStream_t st, double *dot, bool ow) {
+                                          cudaStream_t st, double *dot, bool ow, uint32_t geom) {
   constexpr int p = B200MF_N - 1;
   if (s.number == B200MF_F64)
-    return dot ? launch_bricks_one<p, double, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow)
-               : launch_bricks_one<p, double, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow);
-  return dot ? launch_bricks_one<p, float, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow)
-             : launch_bricks_one<p, float, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow);
+    return dot ? launch_bricks_one<p, double, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom)
+               : launch_bricks_one<p, double, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom);
+  return dot ? launch_bricks_one<p, float, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom)
+             : launch_bricks_one<p, float, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom);
 }
 #endif
 

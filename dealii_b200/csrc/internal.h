@@ -128,7 +128,7 @@ struct Setup {
 
   // bricks (brick_kernel.cuh / brick_setup.cpp): one index per lattice node of every aligned
   // window of brick_b^3 consecutive cells that forms a block; runs of consecutive bricks
-  struct BrickRun { uint64_t cell_begin, cell_end, first_brick; };
+  struct BrickRun { uint64_t cell_begin, cell_end, first_brick; uint32_t geom; };
   uint32_t *d_brick_map = nullptr;
   uint64_t n_bricks = 0;
   // dofs vmult has to zero before its cell loop (all that no brick stores); valid if have_zero_list
@@ -138,6 +138,11 @@ struct Setup {
   int brick_b = 0;
   std::vector<BrickRun> brick_runs;
   double geom0[4] = {0, 0, 0, 0}; // cartesian metric diagonal + det of the single-geometry mesh
+  std::vector<double> h_geom_table;   // cartesian: [n_geom][4] metric diagonal + det (host copy for the bricks)
+  std::vector<uint32_t> h_geom_id;    // per cell, kept while n_geom > 1 (brick detection)
+  // cells that may carry a hanging-node mask all lie in [masked_begin, masked_end): the kernels
+  // without mask handling (plane kernel, sum-factorised diagonal) serve the cells outside
+  uint64_t masked_begin = 0, masked_end = 0;
 
   // bulk brick path (bulk_kernel.cuh / bulk_setup.cpp): pattern tables + per-brick descriptors in
   // execution order, first-toucher-stores write protocol
@@ -206,11 +211,12 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload = true,
 // kernels: the bricks [brick_begin, brick_begin + n_bricks) of the setup
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                   uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
-                  bool overwrite);
+                  bool overwrite, uint32_t geom = 0);
 
 // shape.cpp
 template <typename Number, int n>
-void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrices<Number, n> &out);
+void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrices<Number, n> &out,
+                         uint32_t geom = 0);
 void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
                            std::vector<double> &q_points, std::vector<double> &subface);

@@ -181,7 +181,9 @@ void fill_shape_data(const Setup &s, ShapeData<Number, n> &out) {
 // by the metric of the mesh's single Cartesian cell shape and the operator's constants:
 //   A_cell = g (m0 K(x)M(x)M + m1 M(x)K(x)M + m2 M(x)M(x)K) + c det M(x)M(x)M
 template <typename Number, int n>
-void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrices<Number, n> &out) {
+void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrices<Number, n> &out,
+                         uint32_t geom) {
+  const double *G0 = (s.h_geom_table.size() >= 4 * ((size_t)geom + 1)) ? s.h_geom_table.data() + 4 * (size_t)geom : s.geom0;
   const double *S = s.shape_values.data(), *D = s.shape_grad_colloc.data(), *w = s.q_weights.data();
   double G[n * n], M[n * n], K[n * n];
   for (int i = 0; i < n; ++i)
@@ -213,12 +215,12 @@ void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrice
   symmetrise(K);
   const double g = op.grad_constant;
   const bool has_mass = op.mass_coefficient != nullptr || op.mass_constant != 0.0;
-  const double cm = has_mass ? op.mass_constant * s.geom0[3] : 0.0;
+  const double cm = has_mass ? op.mass_constant * G0[3] : 0.0;
   double Kx[n * n], Ky[n * n], Kz[n * n];
   for (int i = 0; i < n * n; ++i) {
-    Kx[i] = g * s.geom0[0] * K[i];
-    Ky[i] = g * s.geom0[1] * K[i];
-    Kz[i] = g * s.geom0[2] * K[i] + cm * M[i];
+    Kx[i] = g * G0[0] * K[i];
+    Ky[i] = g * G0[1] * K[i];
+    Kz[i] = g * G0[2] * K[i] + cm * M[i];
   }
   pack_eo<Number, n>(M, false, out.M);
   pack_eo<Number, n>(Kx, false, out.Kx);
@@ -227,8 +229,8 @@ void fill_brick_matrices(const Setup &s, const b200mf_operator &op, BrickMatrice
 }
 
 #define INST(N)                                                                     \
-  template void fill_brick_matrices<double, N>(const Setup &, const b200mf_operator &, BrickMatrices<double, N> &); \
-  template void fill_brick_matrices<float, N>(const Setup &, const b200mf_operator &, BrickMatrices<float, N> &);   \
+  template void fill_brick_matrices<double, N>(const Setup &, const b200mf_operator &, BrickMatrices<double, N> &, uint32_t); \
+  template void fill_brick_matrices<float, N>(const Setup &, const b200mf_operator &, BrickMatrices<float, N> &, uint32_t);   \
   template void fill_shape_data<double, N>(const Setup &, ShapeData<double, N> &);  \
   template void fill_shape_data<float, N>(const Setup &, ShapeData<float, N> &);
 INST(2) INST(3) INST(4) INST(5) INST(6) INST(7) INST(8) INST(9)
