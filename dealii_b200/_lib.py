@@ -58,13 +58,21 @@ class SolverDesc(C.Structure):
                 ("chebyshev_degree", C.c_int), ("smoothing_range", C.c_double),
                 ("eig_cg_n_iterations", C.c_int), ("safety_factor", C.c_double),
                 ("tolerance", C.c_double), ("max_iterations", C.c_int),
-                ("first_owned_global_index", u64)]
+                ("first_owned_global_index", u64), ("check_every", C.c_int)]
 
 
 class SolverResult(C.Structure):
     _fields_ = [("iterations", C.c_int), ("residual", C.c_double), ("initial_residual", C.c_double),
                 ("chebyshev_max_eigenvalue", C.c_double), ("chebyshev_min_eigenvalue", C.c_double),
                 ("operator_applications", u64)]
+
+
+class PartitionerInfo(C.Structure):
+    _fields_ = [("n_owned", u64), ("n_ghost", u64), ("n_import", u64),
+                ("n_ghost_targets", C.c_int), ("n_import_targets", C.c_int),
+                ("ghost_target_ranks", C.POINTER(C.c_int)), ("ghost_target_counts", C.POINTER(u64)),
+                ("import_target_ranks", C.POINTER(C.c_int)), ("import_target_counts", C.POINTER(u64)),
+                ("import_indices", u32p)]
 
 
 class MeshDesc(C.Structure):
@@ -118,6 +126,32 @@ SYMBOLS = {
     "b200mf_vec_sadd": (C.c_int, [C.c_int, vp, C.c_double, C.c_double, vp, u64, vp]),
     "b200mf_vec_scale_by": (C.c_int, [C.c_int, vp, vp, vp, u64, vp]),
     "b200mf_vec_dot": (C.c_int, [C.c_int, vp, vp, u64, f64p, vp]),
+    "b200mf_vec_dot_device": (C.c_int, [C.c_int, vp, vp, u64, vp, vp]),
+    "b200mf_vec_norm_sqr": (C.c_int, [C.c_int, vp, u64, f64p, vp]),
+    "b200mf_vec_norm_2": (C.c_int, [C.c_int, vp, u64, f64p, vp]),
+    "b200mf_vec_norm_1": (C.c_int, [C.c_int, vp, u64, f64p, vp]),
+    "b200mf_vec_norm_linfty": (C.c_int, [C.c_int, vp, u64, f64p, vp]),
+    "b200mf_vec_equ": (C.c_int, [C.c_int, vp, C.c_double, vp, C.c_double, vp, u64, vp]),
+    "b200mf_vec_sadd_xavbw": (C.c_int, [C.c_int, vp, C.c_double, C.c_double, vp, C.c_double, vp, u64, vp]),
+    "b200mf_vec_scale": (C.c_int, [C.c_int, vp, C.c_double, vp, u64, vp]),
+    "b200mf_vec_add_and_dot": (C.c_int, [C.c_int, vp, C.c_double, vp, vp, u64, f64p, vp]),
+    "b200mf_comm_get_unique_id": (C.c_int, [vp]),
+    "b200mf_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "b200mf_comm_destroy": (C.c_int, [vp]),
+    "b200mf_comm_allreduce_sum": (C.c_int, [vp, vp, C.c_int, vp]),
+    "b200mf_partitioner_create": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64), u64, C.c_int, C.POINTER(vp)]),
+    "b200mf_partitioner_create_host": (C.c_int, [C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64), u64, C.c_int,
+                                                 C.POINTER(C.c_int), C.POINTER(u64), C.c_int, C.POINTER(u64),
+                                                 C.POINTER(vp)]),
+    "b200mf_partitioner_destroy": (C.c_int, [vp]),
+    "b200mf_partitioner_get_info": (C.c_int, [vp, C.POINTER(PartitionerInfo)]),
+    "b200mf_update_ghost_values": (C.c_int, [vp, vp, vp]),
+    "b200mf_compress_add": (C.c_int, [vp, vp, vp]),
+    "b200mf_zero_out_ghost_values": (C.c_int, [vp, vp, vp]),
+    "b200mf_dist_vmult": (C.c_int, [vp, vp, C.POINTER(Operator), vp, vp, vp]),
+    "b200mf_dist_compute_diagonal": (C.c_int, [vp, vp, C.POINTER(Operator), vp, vp]),
+    "b200mf_dist_cg_solve": (C.c_int, [vp, vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
+                                       C.POINTER(SolverResult), vp]),
     "b200mf_cg_solve": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
                                   C.POINTER(SolverResult), vp]),
     "b200mf_cg_solve_host": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,

@@ -208,6 +208,7 @@ struct CgOptions {
   int max_it;
   bool iteration_number_control; // reaching max_it counts as success
   bool track_eigenvalues;
+  int check_every = 1; // read the residual back only every k-th iteration (not with track_eigenvalues)
 };
 struct CgOutcome {
   int iterations = 0;
@@ -273,6 +274,13 @@ static int cg_fused(Setup &s, const b200mf_operator &op, Number *x, const Number
     out.vmults++;
     cg_post_kernel<Number><<<grid, kVecThreads, 0, st>>>(r, v, d, n, sc, it);
     count_launch();
+    const int every = opt.track_eigenvalues ? 1 : std::max(opt.check_every, 1);
+    if (it % every != 0 && it < opt.max_it) {
+      // no look at the residual this iteration: keep the device busy
+      cg_pre_kernel<Number><<<grid, kVecThreads, 0, st>>>(x, p, r, d, n, sc, it);
+      count_launch();
+      continue;
+    }
     B200MF_CUDA_CHECK(cudaMemcpyAsync(h, sc, 24 * sizeof(double), cudaMemcpyDeviceToHost, st));
     B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
     const double *cur = h + 8 * (it % 3), *nxt = h + 8 * ((it + 1) % 3);
@@ -427,7 +435,7 @@ static int solve_impl(Setup &s, const b200mf_operator &op, const b200mf_solver_d
   Number *x = (Number *)xv;
   const Number *b = (const Number *)bv;
   const Number *d = (const Number *)sd.inverse_diagonal;
-  CgOptions opt{sd.tolerance, sd.max_iterations, false, false};
+  CgOptions opt{sd.tolerance, sd.max_iterations, false, false, sd.check_every};
   CgOutcome out;
   int rc;
   double ev_min = 0.0, ev_max = 0.0;

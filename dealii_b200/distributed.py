@@ -314,24 +314,81 @@ class GhostExchange:
             vec[self.part.n_owned:].zero_()
 
 
-class DistributedMatrixFree:
-    """Portable::MatrixFree on a partitioned mesh: setup + partitioner + overlapped cell loop."""
+class Communicator:
+    """b200mf_comm: one NCCL communicator per process, created from a unique id that rank 0
+    generates and torch.distributed (plumbing only) broadcasts -- a C++ host would MPI_Bcast it."""
 
-    def __init__(self, mesh, number="f64", device="cuda:0", group=None, overlap=True):
-        self.mesh, self.group, self.overlap = mesh, group, overlap
+    def __init__(self, device, group=None):
+        self._lib = L.load()
+        self.n_ranks = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            L.check(self._lib.b200mf_comm_get_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.n_ranks > 1:
+            ident = ident.to(device)
+            dist.broadcast(ident, 0, group=group)
+            ident = ident.cpu()
+        raw = (C.c_ubyte * 128)(*ident.tolist())
+        self._h = C.c_void_p()
+        torch.cuda.set_device(device)
+        L.check(self._lib.b200mf_comm_create(raw, self.n_ranks, self.rank, C.byref(self._h)))
+
+    def allreduce_sum(self, t):
+        L.check(self._lib.b200mf_comm_allreduce_sum(self._h, _ptr(t), t.numel(),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def close(self):
+        if self._h:
+            self._lib.b200mf_comm_destroy(self._h)
+            self._h = None
+
+
+class CPartitioner:
+    """b200mf_partitioner: Utilities::MPI::Partitioner + the ghost exchange of LA::d::Vector, in C."""
+
+    def __init__(self, comm, rank_offsets, ghost_global, number):
+        self._lib, self.comm = L.load(), comm
+        ro = np.ascontiguousarray(rank_offsets, dtype=np.uint64)
+        gg = np.ascontiguousarray(ghost_global, dtype=np.uint64)
+        self._h = C.c_void_p()
+        L.check(self._lib.b200mf_partitioner_create(comm._h, ro.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                    gg.ctypes.data_as(C.POINTER(C.c_uint64)), len(gg),
+                                                    L.F64 if number == "f64" else L.F32, C.byref(self._h)))
+        info = L.PartitionerInfo()
+        L.check(self._lib.b200mf_partitioner_get_info(self._h, C.byref(info)))
+        self.n_owned, self.n_ghost, self.n_import = int(info.n_owned), int(info.n_ghost), int(info.n_import)
+        self.n_ranks, self.rank = comm.n_ranks, comm.rank
+        self.ghost_targets = [(info.ghost_target_ranks[i], int(info.ghost_target_counts[i]))
+                              for i in range(info.n_ghost_targets)]
+        self.import_targets = [(info.import_target_ranks[i], int(info.import_target_counts[i]))
+                               for i in range(info.n_import_targets)]
+
+    def update_ghost_values(self, vec):
+        L.check(self._lib.b200mf_update_ghost_values(self._h, _ptr(vec), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def compress(self, vec):
+        L.check(self._lib.b200mf_compress_add(self._h, _ptr(vec), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def zero_out_ghost_values(self, vec):
+        L.check(self._lib.b200mf_zero_out_ghost_values(self._h, _ptr(vec), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+class DistributedMatrixFree:
+    """Portable::MatrixFree on a partitioned mesh.  Everything on the data path -- partitioner, ghost
+    exchange over NCCL, the overlapped cell loop, the distributed CG -- lives behind the C ABI
+    (csrc/comm.cu: b200mf_comm_*, b200mf_partitioner_*, b200mf_dist_*); this class only binds it."""
+
+    def __init__(self, mesh, number="f64", device="cuda:0", group=None, overlap=True, comm=None):
+        self.mesh, self.group = mesh, group
         self.mf = MatrixFree(number, device).reinit_from_mesh(mesh)
-        self.partitioner = Partitioner(mesh.rank_offsets, mesh.rank, mesh.ghost_global, group=group)
-        self.exchange = GhostExchange(self.partitioner, number, device, group)
+        self.comm = comm if comm is not None else Communicator(self.mf.device, group)
+        self.partitioner = CPartitioner(self.comm, mesh.rank_offsets, mesh.ghost_global, number)
         self.n_owned, self.n_ghost = mesh.n_owned, mesh.n_ghost
         self.n_cells, self.n_interior = mesh.n_cells, mesh.n_cells_interior
-        # high priority: the pack / unpack kernels and (with TORCH_NCCL_HIGH_PRIORITY=1, see the
-        # module docstring) NCCL's transfer kernels take SM slots as CTAs of the cell loop retire
-        self.comm_stream = torch.cuda.Stream(device=self.mf.device, priority=-1)
         self._lib = L.load()
-        # the interior/boundary split must not cut a brick for the store-instead-of-add pieces
-        w = int(self.mf.info.cells_per_brick) if self.mf.info.n_bricks else 1
-        self._brick_cells = max(w, 1)
-        self._pieces_aligned = self.n_interior % self._brick_cells == 0
 
     def initialize_dof_vector(self):
         return self.mf.initialize_dof_vector()
@@ -339,124 +396,35 @@ class DistributedMatrixFree:
     def get_vector_partitioner(self):
         return self.partitioner
 
-    def _range(self, op, dst, src, a, b, dot):
-        if b <= a:
-            return
-        # pieces of one vmult: dst was zeroed by vmult() below and nothing else writes it
+    def vmult(self, op, dst, src):
+        """dst = A src on distributed vectors (b200mf_dist_vmult)."""
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        dp = C.c_void_p(dot) if dot is not None else None
-        if self._pieces_aligned:
-            L.check(self._lib.b200mf_vmult_range(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b, dp, st))
-        else:
-            L.check(self._lib.b200mf_cell_loop_range_dot(self.mf._h, C.byref(op), _ptr(dst), _ptr(src), a, b,
-                                                         dp, st))
-
-    def vmult(self, op, dst, src, dot_ptr=None):
-        """dst = A src on distributed vectors: ghost update || interior cells, cells at the
-        partition boundary, compress || remaining interior cells, copy_constrained_values.
-        dot_ptr: device address of a double accumulating the LOCAL part of src . A src."""
-        main = torch.cuda.current_stream()
-        ex, ni, nc = self.exchange, self.n_interior, self.n_cells
-        single = self.partitioner.n_ranks == 1 or (not ex.ghost_slices and not ex.import_slices)
-        if self._pieces_aligned:
-            L.check(self._lib.b200mf_vmult_prepare(self.mf._h, C.byref(op), _ptr(dst),
-                                                   C.c_void_p(main.cuda_stream)))   # dst = 0 where needed
-        else:
-            dst.zero_()
-        if single:
-            self._range(op, dst, src, 0, nc, dot_ptr)
-        else:
-            w = self._brick_cells
-            half = (ni // 2) // w * w if self.overlap else 0    # pieces of a vmult never cut a brick
-            self.comm_stream.wait_stream(main)
-            with torch.cuda.stream(self.comm_stream):
-                works = ex.update_ghost_values_start(src)
-            self._range(op, dst, src, 0, half, dot_ptr)                    # interior, part A
-            with torch.cuda.stream(self.comm_stream):
-                ex.update_ghost_values_finish(works)
-            main.wait_stream(self.comm_stream)
-            self._range(op, dst, src, ni, nc, dot_ptr)                     # cells touching ghosts
-            self.comm_stream.wait_stream(main)
-            with torch.cuda.stream(self.comm_stream):
-                works = ex.compress_start(dst)
-            self._range(op, dst, src, half, ni, dot_ptr)                   # interior, part B
-            with torch.cuda.stream(self.comm_stream):
-                for w in works:
-                    w.wait()
-            main.wait_stream(self.comm_stream)
-            ex._unpack_add(dst)
-            ex.zero_out_ghost_values(dst)
-            ex.zero_out_ghost_values(src)
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if dot_ptr is None:
-            L.check(self._lib.b200mf_copy_constrained_values(self.mf._h, _ptr(dst), _ptr(src), st))
-        else:
-            L.check(self._lib.b200mf_copy_constrained_values_dot(self.mf._h, _ptr(dst), _ptr(src),
-                                                                 C.c_void_p(dot_ptr), st))
+        L.check(self._lib.b200mf_dist_vmult(self.mf._h, self.partitioner._h, C.byref(op), _ptr(dst), _ptr(src), st))
 
     def compute_diagonal(self, op):
         """MatrixFreeTools::compute_diagonal + compress(add); returns the inverse diagonal."""
         diag = self.initialize_dof_vector()
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        L.check(self._lib.b200mf_compute_diagonal(self.mf._h, C.byref(op), _ptr(diag), st))
-        if self.partitioner.n_ranks > 1:
-            self.exchange.compress(diag)
-            L.check(self._lib.b200mf_set_constrained_values(self.mf._h, _ptr(diag), 1.0, st))
+        L.check(self._lib.b200mf_dist_compute_diagonal(self.mf._h, self.partitioner._h, C.byref(op), _ptr(diag), st))
         inv = torch.zeros_like(diag)
         inv[:self.n_owned] = 1.0 / diag[:self.n_owned]
         return inv
 
 
 def solve_cg(dmf, op, x, b, inverse_diagonal, tolerance, max_iterations, check_every=1):
-    """SolverCG with Jacobi (or no) preconditioner on distributed vectors; returns
-    (iterations, residual, converged).  Same algebra and stopping rule as b200mf_cg_solve /
-    lac/solver_cg.h:703-763; the three partial sums of an iteration are all-reduced where the
-    reference calls Utilities::MPI::sum."""
-    lib, mf = L.load(), dmf.mf
-    n, code = dmf.n_owned, mf._code
-    dev = mf.device
-    multi = dmf.partitioner.n_ranks > 1
-    r, p, v = (dmf.initialize_dof_vector() for _ in range(3))
-    sc = torch.zeros(24, dtype=torch.float64, device=dev)
-    base = sc.data_ptr()
-    d = _ptr(inverse_diagonal) if inverse_diagonal is not None else None
-
-    def stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-    def slot(k):
-        return 8 * (k % 3)
-
-    def allreduce(view):
-        if multi:
-            dist.all_reduce(view, group=dmf.group)
-
-    h = (C.c_double * 1)()
-    L.check(lib.b200mf_vec_dot(code, _ptr(x), _ptr(x), n, h, stream()))
-    xx = torch.tensor([h[0]], dtype=torch.float64, device=dev)
-    allreduce(xx)
-    x_zero = float(xx) == 0.0
-    if not x_zero:
-        dmf.vmult(op, v, x)
-    L.check(lib.b200mf_cg_init(code, _ptr(r), _ptr(p), _ptr(b), None if x_zero else _ptr(v), d, n,
-                               C.c_void_p(base), stream()))
-    allreduce(sc[slot(1) + 1:slot(1) + 3])
-    res = float(sc[slot(1) + 1]) ** 0.5
-    it = 0
-    if res <= tolerance:
-        return 0, res, True
-    while True:
-        it += 1
-        s0, s1 = slot(it), slot(it + 1)
-        dmf.vmult(op, v, p, dot_ptr=base + 8 * s0)
-        allreduce(sc[s0:s0 + 1])
-        L.check(lib.b200mf_cg_post(code, _ptr(r), _ptr(v), d, n, C.c_void_p(base), it, stream()))
-        allreduce(sc[s1 + 1:s1 + 3])
-        done = False
-        if it % check_every == 0 or it >= max_iterations:
-            res = float(sc[s1 + 1]) ** 0.5
-            done = res <= tolerance or it >= max_iterations or res != res
-        if done:
-            L.check(lib.b200mf_cg_final(code, _ptr(x), _ptr(p), n, C.c_void_p(base), it, stream()))
-            return it, res, res <= tolerance
-        L.check(lib.b200mf_cg_pre(code, _ptr(x), _ptr(p), _ptr(r), d, n, C.c_void_p(base), it, stream()))
+    """SolverCG with Jacobi (or no) preconditioner on distributed vectors (b200mf_dist_cg_solve);
+    returns (iterations, residual, converged)."""
+    lib = L.load()
+    sd = L.SolverDesc()
+    sd.tolerance, sd.max_iterations, sd.check_every = tolerance, max_iterations, check_every
+    if inverse_diagonal is not None:
+        sd.preconditioner, sd.inverse_diagonal = L.PRECOND_JACOBI, _ptr(inverse_diagonal)
+    else:
+        sd.preconditioner = L.PRECOND_NONE
+    res = L.SolverResult()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    code = lib.b200mf_dist_cg_solve(dmf.mf._h, dmf.partitioner._h, C.byref(op), C.byref(sd), _ptr(x), _ptr(b),
+                                    C.byref(res), st)
+    if code not in (L.OK, L.ERR_NOCONVERGENCE):
+        L.check(code)
+    return res.iterations, res.residual, code == L.OK

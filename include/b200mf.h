@@ -236,6 +236,25 @@ int b200mf_vec_scale_by(int number, void *y, const void *d, const void *x, uint6
                         void *stream); /* y = d .* x  (DiagonalMatrix::vmult)            */
 int b200mf_vec_dot(int number, const void *x, const void *y, uint64_t n, double *result_host,
                    void *stream);
+/* *result_device += x . y without a host round trip (stays on `stream`)                        */
+int b200mf_vec_dot_device(int number, const void *x, const void *y, uint64_t n, double *result_device,
+                          void *stream);
+/* norm_sqr / l2_norm / l1_norm / linfty_norm (vector_operations_internal.h:2480-2560)           */
+int b200mf_vec_norm_sqr(int number, const void *x, uint64_t n, double *result_host, void *stream);
+int b200mf_vec_norm_2(int number, const void *x, uint64_t n, double *result_host, void *stream);
+int b200mf_vec_norm_1(int number, const void *x, uint64_t n, double *result_host, void *stream);
+int b200mf_vec_norm_linfty(int number, const void *x, uint64_t n, double *result_host, void *stream);
+/* y = a x (+ b v if v != NULL): Vector::equ (Vectorization_equ_au / equ_aubv :2223-2260)         */
+int b200mf_vec_equ(int number, void *y, double a, const void *x, double b, const void *v, uint64_t n,
+                   void *stream);
+/* y = s y + a x + b w: Vector::sadd(s, a, V, b, W) (Vectorization_sadd_xavbw :2312)              */
+int b200mf_vec_sadd_xavbw(int number, void *y, double s, double a, const void *x, double b,
+                          const void *w, uint64_t n, void *stream);
+/* y *= a (d == NULL) or y = y .* d: Vector::operator*= / Vector::scale (:2188, :2338)            */
+int b200mf_vec_scale(int number, void *y, double a, const void *d, uint64_t n, void *stream);
+/* y += a x; returns y . w: Vector::add_and_dot (AddAndDot :2590), the residual update of SolverCG */
+int b200mf_vec_add_and_dot(int number, void *y, double a, const void *x, const void *w, uint64_t n,
+                           double *result_host, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Solver.  SolverCG<LA::d::Vector>::solve (lac/solver_cg.h:1391) with
@@ -256,6 +275,10 @@ typedef struct {
   double tolerance;     /* absolute, on ||r||_2 (SolverControl)                          */
   int max_iterations;
   uint64_t first_owned_global_index; /* for the Chebyshev initial guess (global i % 11)   */
+  /* Jacobi / identity CG: read the residual norm back (one blocking 24-byte copy) only every
+   * check_every iterations; 0 or 1 = every iteration like SolverControl (lac/solver_control.h). With
+   * k > 1 the solve may run up to k - 1 iterations past the tolerance.                           */
+  int check_every;
 } b200mf_solver_desc;
 
 typedef struct {
@@ -316,6 +339,65 @@ int b200mf_ghost_pack(int number, void *buf, const void *vec, const uint32_t *im
                       uint64_t n, void *stream);
 int b200mf_ghost_unpack_add(int number, void *vec, const void *buf,
                             const uint32_t *import_indices, uint64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU: communicator, Utilities::MPI::Partitioner, ghost exchange, distributed cell loop and
+ * distributed CG behind the C ABI (one process per GPU; NCCL over NVLink).
+ * ---------------------------------------------------------------------------------- */
+#define B200MF_UNIQUE_ID_BYTES 128
+typedef struct b200mf_partitioner b200mf_partitioner;
+/* rank 0 calls b200mf_comm_get_unique_id and hands the 128 bytes to the other ranks by any means
+ * (MPI_Bcast in a deal.II host); every rank then calls b200mf_comm_create on ITS current device.  */
+int b200mf_comm_get_unique_id(void *id_out);
+int b200mf_comm_create(const void *unique_id, int n_ranks, int rank, b200mf_comm **out);
+int b200mf_comm_destroy(b200mf_comm *c);
+/* Utilities::MPI::sum of `count` device doubles, in place, on `stream`                            */
+int b200mf_comm_allreduce_sum(b200mf_comm *c, double *device_values, int count, void *stream);
+
+/* Utilities::MPI::Partitioner(locally_owned, ghost_indices, communicator)
+ * (source/base/partitioner.cc:185-330): rank_offsets[r] .. rank_offsets[r+1] is rank r's owned
+ * global range, ghost_global the sorted ghost indices of THIS rank (HOST arrays).  The ghost lists
+ * are exchanged over the communicator to build import_targets / import_indices.                  */
+int b200mf_partitioner_create(b200mf_comm *c, const uint64_t *rank_offsets, const uint64_t *ghost_global,
+                              uint64_t n_ghost, int number, b200mf_partitioner **out);
+/* The same index algebra without a communicator (and without a device): the caller supplies which
+ * ranks ghost which of this rank's dofs (global indices, concatenated in the order of
+ * import_ranks).  Objects built this way cannot exchange.                                        */
+int b200mf_partitioner_create_host(int n_ranks, int rank, const uint64_t *rank_offsets,
+                                   const uint64_t *ghost_global, uint64_t n_ghost, int number,
+                                   const int *import_ranks, const uint64_t *import_counts,
+                                   int n_import_ranks, const uint64_t *import_global,
+                                   b200mf_partitioner **out);
+int b200mf_partitioner_destroy(b200mf_partitioner *p);
+typedef struct {
+  uint64_t n_owned, n_ghost, n_import;
+  int n_ghost_targets, n_import_targets;
+  const int *ghost_target_ranks;        /* Partitioner::ghost_targets(): (rank, count) ascending   */
+  const uint64_t *ghost_target_counts;
+  const int *import_target_ranks;       /* Partitioner::import_targets()                           */
+  const uint64_t *import_target_counts;
+  const uint32_t *import_indices;       /* [n_import] local owned indices, per import target       */
+} b200mf_partitioner_info;
+int b200mf_partitioner_get_info(const b200mf_partitioner *p, b200mf_partitioner_info *info);
+/* LA::d::Vector::update_ghost_values / compress(VectorOperation::add) / zero_out_ghost_values
+ * (lac/la_parallel_vector.templates.h:1026-1332) on `stream`; compress also zeroes the ghosts.    */
+int b200mf_update_ghost_values(const b200mf_partitioner *p, void *vec, void *stream);
+int b200mf_compress_add(const b200mf_partitioner *p, void *vec, void *stream);
+int b200mf_zero_out_ghost_values(const b200mf_partitioner *p, void *vec, void *stream);
+/* Operator::vmult on distributed vectors = Portable::MatrixFree::distributed_cell_loop
+ * (portable_matrix_free.templates.h:1567-1690) inside vmult: dst = 0; update_ghost_values(src)
+ * overlapped with the first half of the interior cells; the cells touching ghosts; compress(dst)
+ * overlapped with the rest of the interior cells; ghosts of src and dst zeroed;
+ * copy_constrained_values.  src is logically const (its ghost section is written and re-zeroed). */
+int b200mf_dist_vmult(const b200mf_setup *s, const b200mf_partitioner *p, const b200mf_operator *op,
+                      void *dst, void *src, void *stream);
+int b200mf_dist_compute_diagonal(const b200mf_setup *s, const b200mf_partitioner *p,
+                                 const b200mf_operator *op, void *diag, void *stream);
+/* SolverCG (PreconditionIdentity / Jacobi) on distributed vectors: b200mf_cg_solve with the partial
+ * sums of every iteration all-reduced (lac/solver_cg.h:871-893, Utilities::MPI::sum).             */
+int b200mf_dist_cg_solve(const b200mf_setup *s, const b200mf_partitioner *p, const b200mf_operator *op,
+                         const b200mf_solver_desc *solver, void *x, const void *b,
+                         b200mf_solver_result *result, void *stream);
 
 /* x and b are HOST arrays of n_owned_dofs elements (copies inside).                      */
 int b200mf_cg_solve_host(const b200mf_setup *s, const b200mf_operator *op,

@@ -230,3 +230,66 @@ def test_global_numbering_matches_the_references_four_rank_run():
     assert len(known) == len(cell_lines) == 9
     for c, expect in zip(known, cell_lines):
         assert cells[c].tolist() == expect, c
+
+
+def _c_partitioner(n_ranks, rank, offsets, ghosts_of_all):
+    """b200mf_partitioner_create_host: the index algebra of the C layer (no communicator, no GPU)."""
+    import ctypes as C
+    from dealii_b200 import _lib as L
+    lib = L.load()
+    ro = np.ascontiguousarray(offsets, dtype=np.uint64)
+    gg = np.ascontiguousarray(ghosts_of_all[rank], dtype=np.uint64)
+    ranks, counts, glob = [], [], []
+    for r in range(n_ranks):
+        if r == rank:
+            continue
+        g = np.asarray(ghosts_of_all[r], dtype=np.uint64)
+        mine = g[(g >= offsets[rank]) & (g < offsets[rank + 1])]
+        if len(mine):
+            ranks.append(r); counts.append(len(mine)); glob.append(mine)
+    ir = (C.c_int * max(len(ranks), 1))(*ranks)
+    ic = (C.c_uint64 * max(len(counts), 1))(*counts)
+    ig = np.ascontiguousarray(np.concatenate(glob) if glob else np.zeros(0), dtype=np.uint64)
+    h = C.c_void_p()
+    L.check(lib.b200mf_partitioner_create_host(n_ranks, rank, ro.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               gg.ctypes.data_as(C.POINTER(C.c_uint64)), len(gg), L.F64, ir, ic,
+                                               len(ranks), ig.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h)))
+    info = L.PartitionerInfo()
+    L.check(lib.b200mf_partitioner_get_info(h, C.byref(info)))
+    out = dict(
+        ghost_targets=[(info.ghost_target_ranks[i], int(info.ghost_target_counts[i])) for i in range(info.n_ghost_targets)],
+        import_targets=[(info.import_target_ranks[i], int(info.import_target_counts[i])) for i in range(info.n_import_targets)],
+        import_indices=[int(info.import_indices[i]) for i in range(info.n_import)], n_import=int(info.n_import))
+    lib.b200mf_partitioner_destroy(h)
+    return out
+
+
+def test_c_partitioner_matches_reference_golden_layout():
+    """The C partitioner (csrc/comm.cu) on the index sets of tests/mpi/parallel_partitioner_03.cc:
+    same ghost_targets / import_targets / import_indices as the Python restatement that reproduces
+    the reference's golden output above."""
+    nproc, s = 4, 200
+    offsets, start = [0], 0
+    for r in range(nproc):
+        start += s - r
+        offsets.append(start)
+    ghosts = np.array([1, 2, 13, s - 2, s - 1, s, s + 1, 2 * s, 2 * s + 1, 2 * s + 3])
+    per_rank = [np.unique(ghosts[(ghosts < offsets[r]) | (ghosts >= offsets[r + 1])]) for r in range(nproc)]
+    for r in range(nproc):
+        py = Partitioner(offsets, r, per_rank[r], all_ghosts=per_rank)
+        c = _c_partitioner(nproc, r, offsets, per_rank)
+        assert c["ghost_targets"] == [(int(a), int(b)) for a, b in py.ghost_targets]
+        assert c["import_targets"] == [(int(a), int(b)) for a, b in py.import_targets]
+        flat = np.concatenate(py.import_indices) if py.import_indices else np.zeros(0, dtype=np.int64)
+        assert c["import_indices"] == [int(v) for v in flat]
+
+
+def test_c_partitioner_on_a_partitioned_mesh():
+    meshes = [PartitionedHyperCubeMesh(3, 2, 2, 8, r, ghost_mode="touched") for r in range(8)]
+    ghosts = [m.ghost_global for m in meshes]
+    for r, m in enumerate(meshes):
+        py = Partitioner(m.rank_offsets, r, m.ghost_global, all_ghosts=ghosts)
+        c = _c_partitioner(8, r, m.rank_offsets, ghosts)
+        assert c["ghost_targets"] == [(int(a), int(b)) for a, b in py.ghost_targets]
+        assert c["import_targets"] == [(int(a), int(b)) for a, b in py.import_targets]
+        assert c["n_import"] == py.n_import
