@@ -43,17 +43,30 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--degree", type=int, default=None)
     ap.add_argument("--refinements", type=int, default=7)
     ap.add_argument("--number", default="f64", choices=["f64", "f32"])
     ap.add_argument("--deformation", type=float, default=0.0)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: BASELINE configs[1] (3D Q4 Laplace, Cartesian hyper_cube); c4: configs[3] (3D Q3 "
+                         "Poisson, one refinement ball per cube = hanging nodes)")
+    ap.add_argument("--ball-radius", type=float, default=0.35)
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-converged-cg", action="store_true")
+    ap.add_argument("--no-chebyshev", action="store_true")
+    ap.add_argument("--cg-rel-tol", type=float, default=1e-6)
+    ap.add_argument("--cg-max-iterations", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ghosts", default="relevant", choices=["relevant", "touched"],
                     help="ghost set: Portable::MatrixFree's locally relevant dofs or the tight touched set")
     ap.add_argument("--cpu-refinements", type=int, default=6,
                     help="per-core sub-cube of the CPU baseline sample")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.degree is None:
+        a.degree = 3 if a.workload == "c4" else 4
+    if a.workload == "c4":
+        a.ghosts = "touched"
+    return a
 
 
 def kernel_name(args, n_bricks=0):
@@ -247,15 +260,30 @@ def run_reference(args):
 
 
 def workload_config(args, n_dofs_total, parallelism):
-    return {"workload": (f"3D Q{args.degree} Laplace vmult, {args.number}, "
-                         f"{'deformed (general cells)' if args.deformation else 'affine Cartesian'} "
-                         f"hyper_cube refine_global({args.refinements}) per GPU"),
+    if getattr(args, "workload", "c2") == "c4":
+        what = (f"3D Q{args.degree} Poisson vmult, {args.number}, hyper_cube refine_global({args.refinements}) + "
+                f"cells within {args.ball_radius} of the cube centre refined once (hanging nodes) per GPU")
+    else:
+        what = (f"3D Q{args.degree} Laplace vmult, {args.number}, "
+                f"{'deformed (general cells)' if args.deformation else 'affine Cartesian'} "
+                f"hyper_cube refine_global({args.refinements}) per GPU")
+    return {"workload": what,
             "degree": args.degree, "dim": 3, "n_dofs_total": int(n_dofs_total),
             "refinements": args.refinements, "parallelism": parallelism,
             "l2": "inputs larger than L2 (vectors >= 1 GB each; no flush needed)"}
 
 
 # ----------------------------------------------------------------------------- engine arm
+def make_mesh(args, world, rank, coarse, dirichlet):
+    from dealii_b200.distributed import AdaptiveHyperCubeMesh, PartitionedHyperCubeMesh
+    if args.workload == "c4":
+        return AdaptiveHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
+                                     ball_radius=args.ball_radius, dirichlet_boundary=dirichlet)
+    return PartitionedHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
+                                    deformation_amplitude=args.deformation, dirichlet_boundary=dirichlet,
+                                    ghost_mode=args.ghosts)
+
+
 def run_engine(args):
     import numpy as np
     import torch
@@ -272,9 +300,8 @@ def run_engine(args):
     if world > 1:
         # NCCL's version / debug banner goes to stdout by default: keep stdout for the JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        # the ghost exchange must get SM slots while the cell-loop kernel has CTAs queued
-        # (tools/dist_diag.py: 2-GPU vmult 1.28 -> 1.18 ms with the NCCL stream at high priority)
-        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+        # torch.distributed is plumbing here (barrier, max over ranks, broadcast of the NCCL id of the
+        # engine's own communicator); the data path is csrc/comm.cu
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
 
@@ -283,19 +310,20 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op="max"):
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t.item())
 
+    max_over_ranks = reduce_ranks
+
     # ---- setup: one cube of the workload per rank, partitioned like p4est
-    from dealii_b200.distributed import DistributedMatrixFree, PartitionedHyperCubeMesh, solve_cg
+    from dealii_b200.distributed import DistributedMatrixFree, solve_cg
     coarse = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world)
     assert coarse is not None, "bench.py supports 1, 2, 4 or 8 GPUs"
-    mesh = PartitionedHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
-                                    deformation_amplitude=args.deformation, ghost_mode=args.ghosts)
+    mesh = make_mesh(args, world, rank, coarse, dirichlet=False)
     dmf = DistributedMatrixFree(mesh, args.number, dev)
     mf = dmf.mf
     op = dealii_b200.LaplaceOperator(mf)
@@ -305,15 +333,45 @@ def run_engine(args):
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
     src = dmf.initialize_dof_vector()
     src[:n_dofs] = torch.rand(n_dofs, dtype=tdt, device=dev, generator=gen)
+    cons = None
+    if args.workload == "c4":      # Portable::MatrixFree semantics: hanging-node entries of src are not read
+        cons = torch.from_numpy(mesh.constrained_dofs.astype(np.int64)).to(dev)
+        src[cons] = 0.0
     dst = dmf.initialize_dof_vector()
 
     def step():
         dmf.vmult(op.op, dst, src)
 
+    # ---- parity self-check inside the bench (every rank count the driver runs proves the NCCL path):
+    # (1) the Laplacian annihilates constants -- needs every ghost value, every hanging-node
+    # interpolation and its transpose, and the compress of the interface rows; (2) symmetry with
+    # partition-independent global sums
+    one = dmf.initialize_dof_vector()
+    one[:n_dofs] = 1.0
+    if cons is not None:
+        one[cons] = 0.0
+    dmf.vmult(op.op, dst, one)
+    if cons is not None:
+        dst[cons] = 0.0
+    inv_diag0 = dmf.compute_diagonal(op.op)
+    defect = reduce_ranks((dst[:n_dofs].abs() * inv_diag0[:n_dofs].abs()).max())
+    v2 = dmf.initialize_dof_vector()
+    v2[:n_dofs] = torch.rand(n_dofs, dtype=tdt, device=dev, generator=gen)
+    if cons is not None:
+        v2[cons] = 0.0
+    w1, w2 = dmf.initialize_dof_vector(), dmf.initialize_dof_vector()
+    dmf.vmult(op.op, w1, src)
+    dmf.vmult(op.op, w2, v2)
+    s12 = reduce_ranks(torch.dot(v2[:n_dofs].double(), w1[:n_dofs].double()), "sum")
+    s21 = reduce_ranks(torch.dot(src[:n_dofs].double(), w2[:n_dofs].double()), "sum")
+    tol_c = 1e-10 if args.number == "f64" else 1e-3
+    parity = {"constants_defect": defect, "symmetry_rel": abs(s12 - s21) / max(abs(s12), 1e-300),
+              "ok": bool(defect < tol_c and abs(s12 - s21) <= tol_c * abs(s12)),
+              "what": "max |A 1| / diag over all rows (0 for the exact operator: ghosts, hanging-node "
+                      "interpolation and compress all enter) and |v.Au - u.Av| / |v.Au| with global sums"}
+    del one, v2, w1, w2, inv_diag0
+
     # ---- value: K vmults, vectors resident in HBM
-    # nvidia-smi needs a few 100 ms to deliver its first sample: start it before the warm-up, keep
-    # the samples from the start of the timed region on, and (below) keep the identical step loop
-    # running untimed until a handful of samples under load exist
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -346,9 +404,9 @@ def run_engine(args):
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline: the cell-loop kernel alone (CUDA events on its stream).  The library says which
-    # brick path its setup-time measurement chose: the bulk brick kernel IS the vmult (one launch,
-    # no memset); the index-map brick kernel is the launch that follows vmult's memset.
+    # ---- roofline: the cell-loop kernel(s) alone (CUDA events on the launching stream).  The library
+    # says which brick path its setup-time measurement chose: the bulk brick kernel IS the vmult (one
+    # launch, no memset); the index-map brick kernel is the launch that follows vmult's memset.
     bulk = mf.bulk_info()
     reps = max(args.steps, 10)
     if bulk["enabled"] and world == 1:
@@ -371,101 +429,92 @@ def run_engine(args):
         bpd += 6 * (bpd / 2) * ((p + 1) / p) ** 3        # merged symmetric metric per q-point
     achieved = bpd * n_dofs / (ms_kernel * 1e-3) / 1e9
     traffic = ncu_traffic()
+    cells_in_bricks = int(mf.info.n_bricks * mf.info.cells_per_brick)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "traffic": (traffic.get("dram_bytes_per_launch") if traffic and args.workload == "c2"
+                            and args.degree == 4 and args.number == "f64" else None),
+                "traffic_source": traffic.get("source") if traffic else None,
                 "kernel": (kernel_name(args, int(mf.info.n_bricks)).replace("brick_cartesian_kernel", "bulk_brick_kernel")
                            if bulk["enabled"] else kernel_name(args, int(mf.info.n_bricks))),
                 "brick_path": {"chosen": "bulk tables + first-toucher-stores" if bulk["enabled"] else
                                "index maps + memset + atomics", "chosen_by": "setup-time measurement",
                                "ms_index_map": bulk["tuned_ms_index_map"], "ms_bulk": bulk["tuned_ms_bulk"],
                                "patterns": bulk["n_patterns"]},
-                "cells_in_bricks": int(mf.info.n_bricks * mf.info.cells_per_brick),
-                "cells": int(mesh.n_cells),
+                "cells_in_bricks": cells_in_bricks, "cells": int(mesh.n_cells),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_dof": bpd, "peak_source": peak_src,
-                "note": ("FP64 sum factorisation is co-bound by the FP64 pipe (37.1 TFLOP/s measured, "
-                         "tools/fp64_peak.cu); see DESIGN.md")}
+                "vmult_frac": bpd * n_dofs / (ms_per_step * 1e-3) / 1e9 / peak,
+                "note": ("kernel_ms = the cell loop over all local cells (all its launches); vmult_frac = the "
+                         "same bytes over the whole vmult (memset, ghost exchange, copy_constrained_values "
+                         "included).  FP64 sum factorisation is co-bound by the FP64 pipe (37.1 TFLOP/s "
+                         "measured, tools/fp64_peak.cu); see DESIGN.md")}
+    if args.workload == "c4":
+        roofline["hanging_node_cells"] = int(mesh.n_masked_cells)
+        roofline["hanging_node_dofs"] = int(mesh.n_hanging_dofs)
 
-    # ---- e2e: host buffers in, host buffers out, copies inside the timed region.  N = 1: the
-    # C-ABI host entry point b200mf_vmult_host; N > 1: the public distributed vmult between a
-    # pinned-host H2D of the owned part and a D2H of the result (ghost exchange included).
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region, through the C ABI:
+    # b200mf_vmult_host_batch (N = 1) / b200mf_dist_vmult_host_batch (N > 1): per vector H2D of the
+    # owned part, vmult (with its ghost exchange), D2H, the copies of neighbouring vectors overlapped
     nbytes = n_dofs * (8 if args.number == "f64" else 4)
-    h_src = torch.empty(n_dofs, dtype=tdt).pin_memory()
-    h_dst = torch.empty(n_dofs, dtype=tdt).pin_memory()
-    h_src.copy_(src[:n_dofs])
-
-    def e2e_step():
-        if world == 1:
-            op.vmult_host(h_dst.numpy(), h_src.numpy())
-        else:
-            src[:n_dofs].copy_(h_src, non_blocking=True)
-            step()
-            h_dst.copy_(dst[:n_dofs], non_blocking=True)
-            torch.cuda.synchronize()
-
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    h_src = [torch.empty(n_dofs, dtype=tdt).pin_memory() for _ in range(2)]
+    h_dst = [torch.empty(n_dofs, dtype=tdt).pin_memory() for _ in range(2)]
+    h_src[0].copy_(src[:n_dofs])
+    h_src[1].copy_(h_src[0])
+    nb = 16 if world == 1 else 8
+    srcs = [h_src[k % 2].numpy() for k in range(nb)]
+    dsts = [h_dst[k % 2].numpy() for k in range(nb)]
+    single = None
+    if world == 1:
+        op.vmult_host(dsts[0], srcs[0])
+        t0 = time.perf_counter()
+        for _ in range(3):
+            op.vmult_host(dsts[0], srcs[0])
+        single = {"value": n_total * 3 / (time.perf_counter() - t0) / 1e9, "api": "b200mf_vmult_host", "steps": 3}
+    dmf.vmult_host_batch(op.op, dsts[:2], srcs[:2])
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    dmf.vmult_host_batch(op.op, dsts, srcs)
     torch.cuda.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": n_total * e2e_steps / t_e2e / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": e2e_steps,
-           "api": ("b200mf_vmult_host (include/b200mf.h)" if world == 1 else
-                   "DistributedMatrixFree.vmult between pinned-host H2D and D2H copies")}
-    if world == 1:
-        # the same through the batched entry point: every vmult still uploads its own input and
-        # downloads its own result, but the copies of neighbouring vmults overlap (the host link is
-        # full duplex) -- the call a user streaming many vectors through the operator makes
-        h_src2 = torch.empty(n_dofs, dtype=tdt).pin_memory()
-        h_dst2 = torch.empty(n_dofs, dtype=tdt).pin_memory()
-        h_src2.copy_(h_src)
-        nb = 16
-        srcs = [(h_src if k % 2 == 0 else h_src2).numpy() for k in range(nb)]
-        dsts = [(h_dst if k % 2 == 0 else h_dst2).numpy() for k in range(nb)]
-        op.vmult_host_batch(dsts[:2], srcs[:2])
-        t0 = time.perf_counter()
-        op.vmult_host_batch(dsts, srcs)
-        t_b = time.perf_counter() - t0
-        e2e = {"value": n_total * nb / t_b / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes, "steps": nb,
-               "api": "b200mf_vmult_host_batch (include/b200mf.h): per-vector H2D, vmult, D2H, pipelined over 2 slots",
-               "single_call": {"value": e2e["value"], "api": e2e["api"], "steps": e2e_steps}}
-        assert float((h_dst2 - h_dst).abs().max()) <= 1e-12 * float(h_dst.abs().max())
-        del h_src2, h_dst2
+    t_b = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": n_total * nb / t_b / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
+           "d2h_bytes_per_step": nbytes * world, "steps": nb,
+           "api": ("b200mf_vmult_host_batch" if world == 1 else "b200mf_dist_vmult_host_batch") +
+                  " (include/b200mf.h): per-vector H2D, vmult, D2H, pipelined over 2 slots"}
+    if single:
+        e2e["single_call"] = single
     step()
     torch.cuda.synchronize()
     # atomics make the summation order (hence the last bits) run-dependent: compare to 1e-12
-    check = float((h_dst[:100000].to(dev) - dst[:100000]).abs().max() / dst[:100000].abs().max())
-    del h_src, h_dst
+    check = float((h_dst[1][:100000].to(dev) - dst[:100000]).abs().max() / dst[:100000].abs().max())
+    del h_src, h_dst, srcs, dsts
 
     # ---- CG + Jacobi (the second half of the metric): DoF-iterations/s
     cg = None
     if not args.no_cg:
-        del dst, src
+        del dst, src, dmf, mf, op
+        torch.cuda.empty_cache()
         cg = run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak)
 
     launches = lc1 - lc0
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del mesh
         r = cpu_reference_sample(args.degree, args.cpu_refinements, 8, 1, args.deformation)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        cfg = workload_config(args, n_total,
+                              "1 GPU" if world == 1 else
+                              f"{world} ranks (1 per GPU), one cube per rank, {mesh.n_ghost} ghost dofs per rank, "
+                              f"NCCL p2p ghost exchange behind the C ABI (b200mf_dist_vmult)")
+        line = {"metric": METRIC if args.workload == "c2" else "vmult_throughput_3d_q3_poisson_hanging_nodes",
+                "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.number, "data": "synthetic",
-                "config": workload_config(args, n_total,
-                                          "1 GPU" if world == 1 else
-                                          f"{world} ranks (1 per GPU), domain decomposition, {args.ghosts} "
-                                          f"ghosts: {mesh.n_ghost} per rank, NCCL p2p exchange"),
+                "dtype": args.number, "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "cg": cg,
-                "e2e_matches_device": bool(check < 1e-12)}
+                "parity_check": parity["ok"], "parity": parity,
+                "e2e_matches_device": bool(check < 1e-12 if args.number == "f64" else check < 1e-5)}
     result = line if rank == 0 else None
     if world > 1:
         dist.destroy_process_group()
@@ -474,13 +523,12 @@ def run_engine(args):
 
 def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
     """SolverCG + Jacobi on the same (partitioned) mesh with zero Dirichlet boundary, rhs = 1:
-    a fixed number of iterations (stopped by max_iterations, like IterationNumberControl)."""
+    (a) a fixed number of iterations (stopped by max_iterations, like IterationNumberControl) for the
+    throughput, (b) a converged solve (time to solution), (c) on one GPU a CG + Chebyshev line."""
     import torch
     import dealii_b200
-    from dealii_b200.distributed import DistributedMatrixFree, PartitionedHyperCubeMesh, solve_cg
-    mesh = PartitionedHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
-                                    deformation_amplitude=args.deformation, dirichlet_boundary=True,
-                                    ghost_mode=args.ghosts)
+    from dealii_b200.distributed import DistributedMatrixFree, solve_cg
+    mesh = make_mesh(args, world, rank, coarse, dirichlet=True)
     dmf = DistributedMatrixFree(mesh, args.number, dev)
     A = dealii_b200.LaplaceOperator(dmf.mf)
     inv_diag = dmf.compute_diagonal(A.op)
@@ -494,18 +542,62 @@ def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        its, res, _ = solve_cg(dmf, A.op, x, b, inv_diag, 1e-300, iters)
+        its, res, _ = solve_cg(dmf, A.op, x, b, inv_diag, 1e-300, iters, check_every=10)
         e1.record()
         torch.cuda.synchronize()
         best = max_over_ranks(e0.elapsed_time(e1))
     n_total = mesh.n_global_dofs
     val = n_total * its / (best * 1e-3) / 1e9
     bpd = CG_BYTES_PER_DOF[args.number]
-    return {"metric": "cg_jacobi_throughput", "value": val, "unit": "GDoF-iterations/s",
-            "iterations": its, "ms_per_iteration": best / max(its, 1), "residual": res,
-            "roofline_frac": bpd * n_total / world * its / (best * 1e-3) / 1e9 / peak,
-            "algorithmic_bytes_per_dof_iteration": bpd,
-            "api": "dealii_b200.distributed.solve_cg (b200mf_cg_* kernels + all-reduce of the CG scalars)"}
+    out = {"metric": "cg_jacobi_throughput", "value": val, "unit": "GDoF-iterations/s",
+           "iterations": its, "ms_per_iteration": best / max(its, 1), "residual": res,
+           "roofline_frac": bpd * n_total / world * its / (best * 1e-3) / 1e9 / peak,
+           "algorithmic_bytes_per_dof_iteration": bpd,
+           "api": "b200mf_dist_cg_solve (include/b200mf.h), residual read back every 10 iterations"}
+    if not args.no_converged_cg:
+        # time to solution: ||r|| <= rel_tol ||b||
+        bn = float(torch.dot(b[:mesh.n_owned].double(), b[:mesh.n_owned].double()))
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([bn], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            bn = float(t)
+        rel = args.cg_rel_tol
+        x = dmf.initialize_dof_vector()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cits, cres, ok = solve_cg(dmf, A.op, x, b, inv_diag, rel * bn ** 0.5, args.cg_max_iterations, check_every=10)
+        e1.record()
+        torch.cuda.synchronize()
+        tsol = max_over_ranks(e0.elapsed_time(e1))
+        out["converged_solve"] = {"relative_tolerance": rel, "iterations": cits, "converged": bool(ok),
+                                  "residual": cres, "seconds": tsol * 1e-3,
+                                  "ms_per_iteration": tsol / max(cits, 1),
+                                  "value": n_total * cits / (tsol * 1e-3) / 1e9, "unit": "GDoF-iterations/s"}
+    if world == 1 and not args.no_chebyshev:
+        # CG with PreconditionChebyshev(degree 3) over Jacobi: 3 operator applications per iteration
+        cheb = dealii_b200.PreconditionChebyshev(degree=3, smoothing_range=20.0, eig_cg_n_iterations=10,
+                                                 preconditioner=dealii_b200.DiagonalMatrix(inv_diag))
+        best = None
+        for rep in range(2):
+            x = dmf.mf.initialize_dof_vector()
+            control = dealii_b200.SolverControl(8, 1e-300)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            try:
+                dealii_b200.SolverCG(control).solve(A, x, b, cheb)
+            except dealii_b200.B200MFError:
+                pass                           # max_iterations reached: that is the stopping rule here
+            e1.record()
+            torch.cuda.synchronize()
+            best = e0.elapsed_time(e1)
+        r = control.last_step()
+        out["chebyshev"] = {"metric": "cg_chebyshev3_throughput", "iterations": r,
+                            "ms_total_incl_eigenvalue_estimate": best,
+                            "note": "SolverCG + PreconditionChebyshev(degree 3, 10 CG iterations for the "
+                                    "eigenvalue estimate) through b200mf_cg_solve"}
+    return out
 
 
 class StdoutForJsonOnly:

@@ -149,6 +149,7 @@ SYMBOLS = {
     "b200mf_compress_add": (C.c_int, [vp, vp, vp]),
     "b200mf_zero_out_ghost_values": (C.c_int, [vp, vp, vp]),
     "b200mf_dist_vmult": (C.c_int, [vp, vp, C.POINTER(Operator), vp, vp, vp]),
+    "b200mf_dist_vmult_host_batch": (C.c_int, [vp, vp, C.POINTER(Operator), C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "b200mf_dist_compute_diagonal": (C.c_int, [vp, vp, C.POINTER(Operator), vp, vp]),
     "b200mf_dist_cg_solve": (C.c_int, [vp, vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
                                        C.POINTER(SolverResult), vp]),

@@ -436,6 +436,49 @@ int b200mf_dist_vmult(const b200mf_setup *h, const b200mf_partitioner *p, const 
   return dist_vmult_impl(h->impl, *p, *op, dst, src, (cudaStream_t)stream, nullptr);
 }
 
+// n_vectors independent distributed vmults on HOST vectors (n_owned elements each, page-locked),
+// pipelined like b200mf_vmult_host_batch: upload of vector k+1 and download of vector k-1 overlap the
+// (ghost-exchanging) vmult of vector k.  Every rank calls it with the same n_vectors.
+int b200mf_dist_vmult_host_batch(const b200mf_setup *h, const b200mf_partitioner *p, const b200mf_operator *op,
+                                 int n_vectors, void *const *dst_host, const void *const *src_host) {
+  B200MF_REQUIRE(h && p && op && n_vectors >= 0 && (n_vectors == 0 || (dst_host && src_host)), "null argument");
+  Setup &s = const_cast<Setup &>(h->impl);
+  const size_t ns = number_size(s.number);
+  const size_t bytes = (s.n_owned + s.n_ghost) * ns, owned_bytes = s.n_owned * ns;
+  for (int i = 0; i < 2; ++i) {
+    if (!s.d_pipe_in[i]) B200MF_CUDA_CHECK(cudaMalloc(&s.d_pipe_in[i], std::max<size_t>(bytes, 1)));
+    if (!s.d_pipe_out[i]) B200MF_CUDA_CHECK(cudaMalloc(&s.d_pipe_out[i], std::max<size_t>(bytes, 1)));
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (!s.pipe_stream[i]) B200MF_CUDA_CHECK(cudaStreamCreateWithFlags(&s.pipe_stream[i], cudaStreamNonBlocking));
+    for (int j = 0; j < 2; ++j)
+      if (!s.pipe_event[i][j]) B200MF_CUDA_CHECK(cudaEventCreateWithFlags(&s.pipe_event[i][j], cudaEventDisableTiming));
+  }
+  cudaStream_t s_in = s.pipe_stream[0], s_op = s.pipe_stream[1], s_out = s.pipe_stream[2];
+  if (s.n_ghost)
+    for (int i = 0; i < 2; ++i)
+      B200MF_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(s.d_pipe_in[i]) + owned_bytes, 0, bytes - owned_bytes, s_in));
+  for (int k = 0; k < n_vectors; ++k) {
+    const int slot = k & 1;
+    B200MF_REQUIRE(dst_host[k] && src_host[k], "null vector in batch");
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_in, s.pipe_event[1][slot], 0));
+    B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_pipe_in[slot], src_host[k], owned_bytes, cudaMemcpyHostToDevice, s_in));
+    B200MF_CUDA_CHECK(cudaEventRecord(s.pipe_event[0][slot], s_in));
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_op, s.pipe_event[0][slot], 0));
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_op, s.pipe_event[2][slot], 0));
+    int rc = dist_vmult_impl(s, *p, *op, s.d_pipe_out[slot], s.d_pipe_in[slot], s_op, nullptr);
+    if (rc != B200MF_OK) return rc;
+    B200MF_CUDA_CHECK(cudaEventRecord(s.pipe_event[1][slot], s_op));
+    B200MF_CUDA_CHECK(cudaStreamWaitEvent(s_out, s.pipe_event[1][slot], 0));
+    B200MF_CUDA_CHECK(cudaMemcpyAsync(dst_host[k], s.d_pipe_out[slot], owned_bytes, cudaMemcpyDeviceToHost, s_out));
+    B200MF_CUDA_CHECK(cudaEventRecord(s.pipe_event[2][slot], s_out));
+  }
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(s_out));
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(s_op));
+  B200MF_CUDA_CHECK(cudaStreamSynchronize(s_in));
+  return B200MF_OK;
+}
+
 int b200mf_dist_compute_diagonal(const b200mf_setup *h, const b200mf_partitioner *p, const b200mf_operator *op,
                                  void *diag, void *stream) {
   B200MF_REQUIRE(h && p && op && diag, "null argument");

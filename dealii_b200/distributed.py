@@ -401,6 +401,13 @@ class DistributedMatrixFree:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         L.check(self._lib.b200mf_dist_vmult(self.mf._h, self.partitioner._h, C.byref(op), _ptr(dst), _ptr(src), st))
 
+    def vmult_host_batch(self, op, dst_hosts, src_hosts):
+        """dst_hosts[k] = A src_hosts[k] for lists of pinned host numpy arrays (owned part)."""
+        n = len(src_hosts)
+        dp = (C.c_void_p * n)(*[d.ctypes.data for d in dst_hosts])
+        sp = (C.c_void_p * n)(*[s.ctypes.data for s in src_hosts])
+        L.check(self._lib.b200mf_dist_vmult_host_batch(self.mf._h, self.partitioner._h, C.byref(op), n, dp, sp))
+
     def compute_diagonal(self, op):
         """MatrixFreeTools::compute_diagonal + compress(add); returns the inverse diagonal."""
         diag = self.initialize_dof_vector()

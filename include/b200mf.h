@@ -391,6 +391,11 @@ int b200mf_zero_out_ghost_values(const b200mf_partitioner *p, void *vec, void *s
  * copy_constrained_values.  src is logically const (its ghost section is written and re-zeroed). */
 int b200mf_dist_vmult(const b200mf_setup *s, const b200mf_partitioner *p, const b200mf_operator *op,
                       void *dst, void *src, void *stream);
+/* b200mf_vmult_host_batch on distributed vectors: every rank streams n_vectors HOST vectors (owned
+ * part, page-locked) through the ghost-exchanging vmult, copies of neighbouring vectors overlapped. */
+int b200mf_dist_vmult_host_batch(const b200mf_setup *s, const b200mf_partitioner *p,
+                                 const b200mf_operator *op, int n_vectors, void *const *dst_host,
+                                 const void *const *src_host);
 int b200mf_dist_compute_diagonal(const b200mf_setup *s, const b200mf_partitioner *p,
                                  const b200mf_operator *op, void *diag, void *stream);
 /* SolverCG (PreconditionIdentity / Jacobi) on distributed vectors: b200mf_cg_solve with the partial
