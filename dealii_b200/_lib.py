@@ -45,7 +45,9 @@ class BulkInfo(C.Structure):
     _fields_ = [("n_bricks", u64), ("n_patterns", u64), ("n_own", u64), ("n_first_scalar", u64),
                 ("n_later", u64), ("n_zero", u64), ("n_general_cells", u64), ("n_boundary_bricks", u64),
                 ("usable", C.c_int), ("enabled", C.c_int),
-                ("tuned_ms_index_map", C.c_double), ("tuned_ms_bulk", C.c_double)]
+                ("tuned_ms_index_map", C.c_double), ("tuned_ms_bulk", C.c_double),
+                ("tuned_ms_coloured", C.c_double), ("n_colours", C.c_int), ("n_coloured_launches", C.c_int),
+                ("n_zero_coloured", u64), ("path", C.c_int)]
 
 
 class Operator(C.Structure):
@@ -170,6 +172,7 @@ SYMBOLS = {
     "b200mf_brick_probe": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
     "b200mf_bulk_probe": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(BulkInfo)]),
     "b200mf_setup_enable_bulk": (C.c_int, [vp, C.c_int]),
+    "b200mf_setup_select_brick_path": (C.c_int, [vp, C.c_int]),
     "b200mf_setup_get_bulk_info": (C.c_int, [vp, C.POINTER(BulkInfo)]),
     "b200mf_vmult_prepare": (C.c_int, [vp, C.POINTER(Operator), vp, vp]),
     "b200mf_vmult_range": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),

@@ -33,7 +33,7 @@ DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 #define DECL_N(N)                                                                              \
   int launch_bricks_n##N(const Setup &, const b200mf_operator &, void *, const void *, uint64_t, \
-                         uint64_t, cudaStream_t, double *, bool, uint32_t);
+                         uint64_t, cudaStream_t, double *, bool, uint32_t, const uint32_t *);
 DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 
@@ -63,16 +63,17 @@ DECL_N(2) DECL_N(3) DECL_N(4) DECL_N(5) DECL_N(6) DECL_N(7) DECL_N(8) DECL_N(9)
 #undef DECL_N
 
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
-                  uint64_t bb, uint64_t nb, cudaStream_t st, double *dot, bool ow, uint32_t geom) {
+                  uint64_t bb, uint64_t nb, cudaStream_t st, double *dot, bool ow, uint32_t geom,
+                  const uint32_t *list) {
   switch (s.n) {
-    case 2: return launch_bricks_n2(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 3: return launch_bricks_n3(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 4: return launch_bricks_n4(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 5: return launch_bricks_n5(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 6: return launch_bricks_n6(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 7: return launch_bricks_n7(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 8: return launch_bricks_n8(s, op, dst, src, bb, nb, st, dot, ow, geom);
-    case 9: return launch_bricks_n9(s, op, dst, src, bb, nb, st, dot, ow, geom);
+    case 2: return launch_bricks_n2(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 3: return launch_bricks_n3(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 4: return launch_bricks_n4(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 5: return launch_bricks_n5(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 6: return launch_bricks_n6(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 7: return launch_bricks_n7(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 8: return launch_bricks_n8(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
+    case 9: return launch_bricks_n9(s, op, dst, src, bb, nb, st, dot, ow, geom, list);
   }
   set_error("unsupported degree %d", s.degree);
   return B200MF_ERR_UNSUPPORTED;
@@ -496,6 +497,44 @@ int vmult_prepare_impl(const Setup &s, const b200mf_operator &op, void *dst, cud
   return B200MF_OK;
 }
 
+bool coloured_enabled(const Setup &s, const b200mf_operator &op) {
+  return s.colouring.ready && s.colouring.enabled && bricks_enabled(s, op);
+}
+
+// zero what no brick stores (ghost section, dofs of the per-cell kernels, untouched dofs)
+int coloured_prepare(const Setup &s, void *dst, cudaStream_t st) {
+  const Setup::Colouring &K = s.colouring;
+  const size_t ns = number_size(s.number);
+  if (s.n_ghost)
+    B200MF_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(dst) + s.n_owned * ns, 0, s.n_ghost * ns, st));
+  if (K.n_zero) {
+    const unsigned blocks = (unsigned)((K.n_zero + 255) / 256);
+    if (s.number == B200MF_F64)
+      set_constrained_kernel<double><<<blocks, 256, 0, st>>>((double *)dst, 0.0, K.d_zero, K.n_zero);
+    else
+      set_constrained_kernel<float><<<blocks, 256, 0, st>>>((float *)dst, 0.0f, K.d_zero, K.n_zero);
+    count_launch();
+    B200MF_CUDA_CHECK(cudaGetLastError());
+  }
+  return B200MF_OK;
+}
+
+int launch_coloured(const Setup &s, const b200mf_operator &op, void *dst, const void *src, int piece,
+                    cudaStream_t st, double *dot_accum) {
+  const Setup::Colouring &K = s.colouring;
+  for (const auto &r : K.general) {
+    if (piece >= 0 && r.piece != piece) continue;
+    int rc = launch_cells(s, op, dst, src, r.begin, r.end, st, false, dot_accum);
+    if (rc != B200MF_OK) return rc;
+  }
+  for (const auto &l : K.launches) {
+    if (piece >= 0 && l.piece != piece) continue;
+    int rc = launch_bricks(s, op, dst, src, l.offset, l.count, st, dot_accum, true, l.geom, K.d_list);
+    if (rc != B200MF_OK) return rc;
+  }
+  return B200MF_OK;
+}
+
 // bulk brick path usable for this call?  (bulk copies need 16-byte aligned vectors)
 bool bulk_enabled(const Setup &s, const b200mf_operator &op, const void *dst, const void *src) {
   static const bool legacy = std::getenv("B200MF_KERNEL") != nullptr && std::string(std::getenv("B200MF_KERNEL")) == "brick";
@@ -531,6 +570,13 @@ int vmult_impl(const Setup &s, const b200mf_operator &op, void *dst, const void 
                cudaStream_t st, double *dot_accum) {
   if (bulk_enabled(s, op, dst, src)) {
     int rc = vmult_bulk_impl(s, op, dst, src, st, dot_accum);
+    if (rc != B200MF_OK) return rc;
+    return copy_constrained_impl(s, dst, src, st, dot_accum);
+  }
+  if (coloured_enabled(s, op)) {
+    int rc = coloured_prepare(s, dst, st);
+    if (rc != B200MF_OK) return rc;
+    rc = launch_coloured(s, op, dst, src, -1, st, dot_accum);
     if (rc != B200MF_OK) return rc;
     return copy_constrained_impl(s, dst, src, st, dot_accum);
   }
@@ -739,41 +785,51 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   // index-map brick path (memset + atomics on shared dofs) and the bulk brick path
   // (first-toucher-stores, no memset), time a few vmults of each on scratch vectors and keep the
   // faster one.  B200MF_BULK=0/1 forces the choice.
-  if (s.bulk.ready) {
-    const char *force = std::getenv("B200MF_BULK");
+  if (s.bulk.ready || s.colouring.ready) {
+    // candidates: 0 = index maps + memset + atomics, 1 = coloured launches (no atomics, no memset),
+    // 2 = bulk tables + first-toucher-stores in one launch
+    const char *force = std::getenv("B200MF_BRICK_PATH");
+    auto select = [&](int path) {
+      s.colouring.enabled = path == 1;
+      s.bulk.enabled = path == 2;
+    };
     if (force != nullptr) {
-      s.bulk.enabled = std::atoi(force) != 0;
+      select(std::atoi(force));
     } else {
       const size_t bytes = (s.n_owned + s.n_ghost) * number_size(s.number);
       void *va = nullptr, *vb = nullptr;
+      int best = 0;
       if (cudaMalloc(&va, bytes) == cudaSuccess && cudaMalloc(&vb, bytes) == cudaSuccess) {
         cudaMemset(va, 0, bytes);
         b200mf_operator op{nullptr, nullptr, 1.0, 0.0};
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        float ms[2] = {0.f, 0.f};
-        for (int mode = 0; mode < 2 && rc == B200MF_OK; ++mode) {
-          s.bulk.enabled = mode == 1;
+        float ms[3] = {0.f, 0.f, 0.f};
+        for (int mode = 0; mode < 3 && rc == B200MF_OK; ++mode) {
+          if ((mode == 1 && !s.colouring.ready) || (mode == 2 && !s.bulk.ready)) continue;
+          select(mode);
           for (int i = 0; i < 2 && rc == B200MF_OK; ++i) rc = vmult_impl(s, op, vb, va, nullptr, nullptr);
           cudaEventRecord(e0, nullptr);
           for (int i = 0; i < 4 && rc == B200MF_OK; ++i) rc = vmult_impl(s, op, vb, va, nullptr, nullptr);
           cudaEventRecord(e1, nullptr);
           cudaEventSynchronize(e1);
           cudaEventElapsedTime(&ms[mode], e0, e1);
+          ms[mode] /= 4;
+          if (rc == B200MF_OK && ms[mode] < ms[best]) best = mode;
         }
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-        s.bulk.enabled = rc == B200MF_OK && ms[1] < ms[0];
-        s.bulk.tuned_ms[0] = ms[0] / 4;
-        s.bulk.tuned_ms[1] = ms[1] / 4;
+        s.bulk.tuned_ms[0] = ms[0];
+        s.colouring.tuned_ms = ms[1];
+        s.bulk.tuned_ms[1] = ms[2];
         rc = B200MF_OK;
       } else {
-        s.bulk.enabled = false;
         (void)cudaGetLastError();
       }
       cudaFree(va);
       cudaFree(vb);
+      select(best);
     }
   }
   B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_scratch, 4096 * sizeof(double)));
@@ -791,6 +847,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
   cudaFree(s->d_diag_tables);
   cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map); cudaFree(s->d_zero_list);
+  cudaFree(s->colouring.d_list); cudaFree(s->colouring.d_zero);
   free_bulk(*s);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);
@@ -921,7 +978,17 @@ int b200mf_bulk_probe(const b200mf_setup_desc *d, b200mf_bulk_info *info) {
 int b200mf_setup_enable_bulk(b200mf_setup *h, int enable) {
   B200MF_REQUIRE(h, "null argument");
   h->impl.bulk.enabled = enable != 0;
+  h->impl.colouring.enabled = false;
   return h->impl.bulk.ready ? 1 : 0;
+}
+
+int b200mf_setup_select_brick_path(b200mf_setup *h, int path) {
+  B200MF_REQUIRE(h && path >= 0 && path <= 2, "bad argument");
+  Setup &s = h->impl;
+  if ((path == 1 && !s.colouring.ready) || (path == 2 && !s.bulk.ready)) return -1;
+  s.colouring.enabled = path == 1;
+  s.bulk.enabled = path == 2;
+  return path;
 }
 
 int b200mf_setup_get_bulk_info(const b200mf_setup *h, b200mf_bulk_info *info) {
@@ -934,6 +1001,11 @@ int b200mf_setup_get_bulk_info(const b200mf_setup *h, b200mf_bulk_info *info) {
   info->enabled = h->impl.bulk.ready && h->impl.bulk.enabled ? 1 : 0;
   info->tuned_ms_index_map = h->impl.bulk.tuned_ms[0];
   info->tuned_ms_bulk = h->impl.bulk.tuned_ms[1];
+  info->tuned_ms_coloured = h->impl.colouring.tuned_ms;
+  info->n_colours = h->impl.colouring.ready ? h->impl.colouring.n_colours : 0;
+  info->n_coloured_launches = (int)h->impl.colouring.launches.size();
+  info->n_zero_coloured = h->impl.colouring.n_zero;
+  info->path = (h->impl.bulk.ready && h->impl.bulk.enabled) ? 2 : ((h->impl.colouring.ready && h->impl.colouring.enabled) ? 1 : 0);
   return B200MF_OK;
 }
 

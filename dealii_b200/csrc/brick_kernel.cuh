@@ -32,7 +32,8 @@
 namespace b200mf {
 
 #define B200MF_MAP_COMPLETE 0x40000000u
-#define B200MF_MAP_INDEX 0x3fffffffu
+#define B200MF_MAP_FIRST 0x20000000u
+#define B200MF_MAP_INDEX 0x1fffffffu
 
 template <int p, int b, typename Number>
 struct BrickCfg {
@@ -115,7 +116,10 @@ struct BrickKernelParams {
   Number *dst;
   double *dot_accum; // optional: += src . (A src) over these bricks
   unsigned long long brick_begin;
-  int overwrite; // 1: dst is known to be zero (vmult) -> complete dofs are stored, not added
+  const uint32_t *list; // optional: brick ids of this launch (coloured launches)
+  // 0: add into dst; 1: dst is known to be zero (vmult) -> complete dofs are stored, the others use
+  // RED; 2: coloured launch: complete / first-toucher dofs are stored, the others load-add-store
+  int overwrite;
 };
 
 template <int p, int b, typename Number, bool DOT>
@@ -130,7 +134,9 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
   Number *P0 = reinterpret_cast<Number *>(brick_smem);
   Number *P1 = P0 + L3;
   const int tid = threadIdx.x;
-  const uint32_t *__restrict__ map = prm.map + (prm.brick_begin + blockIdx.x) * (unsigned long long)L3;
+  const unsigned long long brick = prm.list ? (unsigned long long)__ldg(prm.list + prm.brick_begin + blockIdx.x)
+                                            : prm.brick_begin + blockIdx.x;
+  const uint32_t *__restrict__ map = prm.map + brick * (unsigned long long)L3;
   const Number *__restrict__ src = prm.src;
 
   // ---- read_dof_values of the whole brick: every lattice node once
@@ -194,6 +200,14 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
   if (active) {
 #pragma unroll
     for (int z = 0; z < L; ++z) mz[z] = __ldg(map + tid + z * L2);
+    if (prm.overwrite == 2) {
+      // coloured launch: the dofs an earlier launch stored are read back at scatter time; ask L2
+      // for them now so that the reads do not sit on the critical path of the z sweep
+#pragma unroll
+      for (int z = 0; z < L; ++z)
+        if ((mz[z] & (CBIT | B200MF_MAP_COMPLETE | B200MF_MAP_FIRST)) == 0)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.dst + (mz[z] & B200MF_MAP_INDEX)));
+    }
   }
 
   // ---- y sweep: C = My A -> P0, D = Ky A + My B -> P1 (both in place); thread <-> (x, z)
@@ -245,7 +259,7 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
     auto emit = [&](uint32_t m, Number v, Number u, Number o) {
       if (!(m & CBIT)) {
         Number *d = dst + (m & B200MF_MAP_INDEX);
-        if (m & B200MF_MAP_COMPLETE) *d = v + o;
+        if ((m & B200MF_MAP_COMPLETE) || prm.overwrite == 2) *d = v + o;
         else atomicAdd(d, v);
         if (DOT) dot += double(u) * double(v);
       }
@@ -261,12 +275,15 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
         for (int k = 0; k < p; ++k)
           ui[k] = (mz[c * p + k] & CBIT) ? Number(0) : __ldg(src + (mz[c * p + k] & B200MF_MAP_INDEX));
       }
-      if (!prm.overwrite) {
+      // values already in dst that this brick adds to, requested before the block's arithmetic:
+      // cell_loop mode adds into the complete dofs (the others go through RED), a coloured launch
+      // adds into the dofs an earlier launch stored (no atomics: bricks of a colour share no dof)
+      if (prm.overwrite != 1) {
+        const uint32_t want = prm.overwrite == 2 ? 0u : B200MF_MAP_COMPLETE;
+        const uint32_t bits = prm.overwrite == 2 ? (CBIT | B200MF_MAP_COMPLETE | B200MF_MAP_FIRST) : (CBIT | B200MF_MAP_COMPLETE);
 #pragma unroll
         for (int k = 0; k < p; ++k)
-          old[k] = (mz[c * p + k] & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE
-                       ? dst[mz[c * p + k] & B200MF_MAP_INDEX]
-                       : Number(0);
+          old[k] = (mz[c * p + k] & bits) == want ? dst[mz[c * p + k] & B200MF_MAP_INDEX] : Number(0);
       }
 #pragma unroll
       for (int k = 1; k < n; ++k) {
@@ -284,7 +301,7 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
       if (c > 0) oV[0] += cV;
 #pragma unroll
       for (int k = 0; k < p; ++k)
-        emit(mz[c * p + k], oV[k], DOT ? ui[k] : Number(0), prm.overwrite ? Number(0) : old[k]);
+        emit(mz[c * p + k], oV[k], DOT ? ui[k] : Number(0), prm.overwrite == 1 ? Number(0) : old[k]);
       cV = oV[p];
       inC[0] = inC[p];
       inD[0] = inD[p];
@@ -294,7 +311,8 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
       Number u = Number(0);
       if (DOT && !(m & CBIT)) u = __ldg(src + (m & B200MF_MAP_INDEX));
       Number o = Number(0);
-      if (!prm.overwrite && (m & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE)
+      if ((prm.overwrite == 0 && (m & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE) ||
+          (prm.overwrite == 2 && (m & (CBIT | B200MF_MAP_COMPLETE | B200MF_MAP_FIRST)) == 0))
         o = dst[m & B200MF_MAP_INDEX];
       emit(m, cV, u, o);
     }

@@ -26,9 +26,138 @@ inline void morton_decode(unsigned c, int &x, int &y, int &z) {
 }
 } // namespace
 
+// Colouring of the bricks -- the alternative to "memset + atomics" the reference offers as graph
+// colouring (portable_matrix_free.templates.h:1060-1185, portable_fe_evaluation.h:410-435): bricks
+// of one colour share no dof and run in one launch, colours run one after the other, so the
+// surface dofs need no atomics.  On top of the reference's scheme the FIRST brick (in launch order)
+// that touches a dof STORES it -- flagged in the map -- so vmult needs no memset of dst either; later
+// touchers do a plain load-add-store.  Results are bit-reproducible.  Launch order = piece of the
+// distributed schedule (first half of the interior | cells touching ghosts | rest of the interior),
+// then cell shape, then colour.  Dofs that a cell outside the bricks touches, ghost dofs and dofs
+// nobody stores are zeroed before the vmult (zero list + memset of the ghost section).
+static int build_colouring(const b200mf_setup_desc &d, Setup &s, std::vector<uint32_t> &maps, uint64_t nb,
+                           const std::vector<uint64_t> &brick_cell, const std::vector<uint32_t> &brick_geom) {
+  constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, COMPLETE = 0x40000000u;
+  Setup::Colouring &K = s.colouring;
+  K = Setup::Colouring();
+  if (nb == 0 || std::getenv("B200MF_NO_COLOURING") != nullptr) return B200MF_OK;
+  const int p = s.degree, n = s.n, b = s.brick_b ? s.brick_b : brick_edge(s.degree);
+  const int L = b * p + 1;
+  const uint64_t L3 = (uint64_t)L * L * L, W = (uint64_t)b * b * b, npc = (uint64_t)n * n * n;
+  const uint64_t n_total = s.n_owned + s.n_ghost;
+  const uint64_t ni = (s.n_cells_interior > 0 && s.n_cells_interior < s.n_cells) ? s.n_cells_interior : s.n_cells;
+  const bool pieces = s.n_ghost > 0 && ni < s.n_cells;
+  K.half = pieces ? (ni / 2) / W * W : ni;
+  auto piece_of_cell = [&](uint64_t c) -> int { return !pieces ? 0 : (c >= ni ? 1 : (c < K.half ? 0 : 2)); };
+  // dofs the per-cell kernels accumulate into (atomics on zeroed entries): never stored by a brick
+  std::vector<uint8_t> early(n_total, 0);
+  for (uint64_t i = s.n_owned; i < n_total; ++i) early[i] = 1;
+  {
+    std::vector<uint8_t> in_brick(s.n_cells, 0);
+    for (uint64_t w = 0; w < nb; ++w)
+      for (uint64_t c = 0; c < W; ++c) in_brick[brick_cell[w] + c] = 1;
+    for (uint64_t c = 0; c < s.n_cells; ++c) {
+      if (in_brick[c]) continue;
+      for (uint64_t e = c * npc; e < (c + 1) * npc; ++e) {
+        const uint32_t v = d.local_to_global[e];
+        if (!(v & CBIT) && v < n_total) early[v] = 1;
+      }
+    }
+  }
+  // greedy colouring in brick order: a colour is free if no brick sharing a dof has it
+  std::vector<uint32_t> used(n_total, 0); // per dof: colours of the bricks touching it
+  std::vector<uint8_t> colour(nb, 0);
+  int n_colours = 0;
+  for (uint64_t w = 0; w < nb; ++w) {
+    const uint32_t *m = maps.data() + w * L3;
+    uint32_t forbidden = 0;
+    for (uint64_t e = 0; e < L3; ++e)
+      if (!(m[e] & (CBIT | COMPLETE))) forbidden |= used[m[e] & B200MF_BRICK_INDEX];
+    int c = 0;
+    while (c < 32 && (forbidden >> c) & 1u) ++c;
+    if (c >= 32) return B200MF_OK; // no colouring: the atomics path serves the setup
+    colour[w] = (uint8_t)c;
+    n_colours = std::max(n_colours, c + 1);
+    for (uint64_t e = 0; e < L3; ++e)
+      if (!(m[e] & (CBIT | COMPLETE))) used[m[e] & B200MF_BRICK_INDEX] |= 1u << c;
+  }
+  used.clear();
+  used.shrink_to_fit();
+  // launch key of a brick and the smallest key among the touchers of every dof
+  auto key_of = [&](uint64_t w) -> uint32_t {
+    return ((uint32_t)piece_of_cell(brick_cell[w]) << 16) | (brick_geom[w] << 8) | colour[w];
+  };
+  std::vector<uint32_t> min_key(n_total, 0xffffffffu);
+  for (uint64_t w = 0; w < nb; ++w) {
+    const uint32_t *m = maps.data() + w * L3, k = key_of(w);
+    for (uint64_t e = 0; e < L3; ++e)
+      if (!(m[e] & (CBIT | COMPLETE))) {
+        uint32_t &mk = min_key[m[e] & B200MF_BRICK_INDEX];
+        mk = std::min(mk, k);
+      }
+  }
+  std::vector<uint8_t> stored(n_total, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t w = 0; w < (int64_t)nb; ++w) {
+    uint32_t *m = maps.data() + (uint64_t)w * L3;
+    const uint32_t k = key_of(w);
+    for (uint64_t e = 0; e < L3; ++e) {
+      if (m[e] & CBIT) continue;
+      const uint32_t v = m[e] & B200MF_BRICK_INDEX;
+      if (m[e] & COMPLETE) { stored[v] = 1; continue; }
+      if (!early[v] && min_key[v] == k) {
+        m[e] |= B200MF_BRICK_FIRST;
+        stored[v] = 1;
+      }
+    }
+  }
+  // launches: bricks sorted by key, one launch per key
+  std::vector<uint32_t> order(nb);
+  for (uint64_t w = 0; w < nb; ++w) order[w] = (uint32_t)w;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return key_of(a) < key_of(c); });
+  for (uint64_t i = 0; i < nb;) {
+    uint64_t j = i;
+    const uint32_t k = key_of(order[i]);
+    while (j < nb && key_of(order[j]) == k) ++j;
+    K.launches.push_back({(int)(k >> 16), (k >> 8) & 0xffu, i, j - i});
+    i = j;
+  }
+  std::vector<uint32_t> zero_list;
+  for (uint64_t i = 0; i < s.n_owned; ++i)
+    if (!stored[i]) zero_list.push_back((uint32_t)i);
+  K.n_zero = zero_list.size();
+  K.n_colours = n_colours;
+  // cells outside the bricks, per piece
+  {
+    uint64_t pos = 0;
+    auto add = [&](uint64_t cb, uint64_t ce) {
+      // split at the piece boundaries
+      const uint64_t cuts[4] = {0, K.half, ni, s.n_cells};
+      for (int q = 0; q < 3; ++q) {
+        const uint64_t a = std::max(cb, cuts[q]), e = std::min(ce, cuts[q + 1]);
+        if (e > a) K.general.push_back({piece_of_cell(a), a, e});
+      }
+    };
+    for (const Setup::BrickRun &run : s.brick_runs) {
+      add(pos, run.cell_begin);
+      pos = run.cell_end;
+    }
+    add(pos, s.n_cells);
+  }
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&K.d_list, nb * sizeof(uint32_t)));
+  B200MF_CUDA_CHECK(cudaMemcpy(K.d_list, order.data(), nb * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&K.d_zero, std::max<size_t>(zero_list.size(), 1) * sizeof(uint32_t)));
+  B200MF_CUDA_CHECK(cudaMemcpy(K.d_zero, zero_list.data(), zero_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  s.device_bytes += (nb + zero_list.size()) * sizeof(uint32_t);
+  s.index_bytes += (nb + zero_list.size()) * sizeof(uint32_t);
+  K.ready = true;
+  return B200MF_OK;
+}
+
 // Fills s.brick_* ; returns B200MF_OK also when no brick was found.
 int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_complete_out,
                  BulkStats *bulk_stats) {
+  s.brick_b = brick_edge(s.degree);
   constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, COMPLETE = 0x40000000u, UNSET = 0xffffffffu;
   s.n_bricks = 0;
   s.brick_runs.clear();
@@ -38,11 +167,17 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   const uint32_t *gid = (s.n_geom > 1 && s.h_geom_id.size() == s.n_cells) ? s.h_geom_id.data() : nullptr;
   if (s.n_geom > 1 && gid == nullptr) return B200MF_OK;
   const uint64_t n_total = s.n_owned + s.n_ghost;
-  if (n_total >= COMPLETE) return B200MF_OK;
+  if (n_total >= B200MF_BRICK_FIRST) return B200MF_OK; // bits 29..31 of a map entry are flags
   const int p = s.degree, n = s.n, b = brick_edge(s.degree);
   const int L = b * p + 1, L2 = L * L;
   const uint64_t L3 = (uint64_t)L2 * L, W = (uint64_t)b * b * b, npc = (uint64_t)n * n * n;
-  const uint64_t n_windows = s.n_cells / W;
+  // aligned windows of W consecutive cells: aligned to cell 0 inside the interior class and to
+  // n_cells_interior behind it (the generators emit whole blocks first in both classes)
+  const uint64_t ni_split = (s.n_cells_interior > 0 && s.n_cells_interior < s.n_cells) ? s.n_cells_interior : s.n_cells;
+  std::vector<uint64_t> win_cell; // first cell of every window
+  for (uint64_t c = 0; c + W <= ni_split; c += W) win_cell.push_back(c);
+  for (uint64_t c = ni_split; c + W <= s.n_cells; c += W) win_cell.push_back(c);
+  const uint64_t n_windows = win_cell.size();
   if (n_windows == 0) return B200MF_OK;
   const uint32_t *l2g = d.local_to_global;
 
@@ -79,12 +214,13 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
     uint32_t *lat = maps.data() + (uint64_t)w * L3;
     std::fill(lat, lat + L3, UNSET);
     bool good = true;
+    const uint64_t wc = win_cell[w];
     if (cmask)
-      for (unsigned c = 0; c < W && good; ++c) good = cmask[(uint64_t)w * W + c] == 0;
+      for (unsigned c = 0; c < W && good; ++c) good = cmask[wc + c] == 0;
     if (gid)
-      for (unsigned c = 1; c < W && good; ++c) good = gid[(uint64_t)w * W + c] == gid[(uint64_t)w * W];
+      for (unsigned c = 1; c < W && good; ++c) good = gid[wc + c] == gid[wc];
     for (unsigned c = 0; c < W && good; ++c) {
-      const uint32_t *cl = l2g + ((uint64_t)w * W + c) * npc;
+      const uint32_t *cl = l2g + (wc + c) * npc;
       const int ox = cx[c] * p, oy = cy[c] * p, oz = cz[c] * p;
       for (int k = 0; k < n && good; ++k)
         for (int j = 0; j < n && good; ++j)
@@ -110,14 +246,19 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
 
   // compact the maps of the accepted windows and record the runs of consecutive bricks
   uint64_t nb = 0;
+  std::vector<uint64_t> brick_cell;
+  std::vector<uint32_t> brick_geom;
   for (uint64_t w = 0; w < n_windows; ++w) {
     if (!ok[w]) continue;
     if (nb != w) std::memmove(maps.data() + nb * L3, maps.data() + w * L3, L3 * sizeof(uint32_t));
-    const uint32_t g = gid ? gid[w * W] : 0u;
-    if (!s.brick_runs.empty() && s.brick_runs.back().cell_end == w * W && s.brick_runs.back().geom == g)
-      s.brick_runs.back().cell_end = (w + 1) * W;
+    const uint64_t wc = win_cell[w];
+    const uint32_t g = gid ? gid[wc] : 0u;
+    if (!s.brick_runs.empty() && s.brick_runs.back().cell_end == wc && s.brick_runs.back().geom == g)
+      s.brick_runs.back().cell_end = wc + W;
     else
-      s.brick_runs.push_back({w * W, (w + 1) * W, nb, g});
+      s.brick_runs.push_back({wc, wc + W, nb, g});
+    brick_cell.push_back(wc);
+    brick_geom.push_back(g);
     ++nb;
   }
   if (n_complete_out) {
@@ -145,7 +286,7 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < (int64_t)(nb * L3); ++e) {
       const uint32_t v = maps[e];
-      if (!(v & CBIT) && (v & COMPLETE)) complete[v & 0x3fffffffu] = 1;
+      if (!(v & CBIT) && (v & COMPLETE)) complete[v & B200MF_BRICK_INDEX] = 1;
     }
     std::vector<uint32_t> zero_list;
     for (uint64_t i = 0; i < n_total; ++i)
@@ -160,6 +301,9 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
       s.index_bytes += zero_list.size() * sizeof(uint32_t);
     }
   }
+  maps.resize(nb * L3);
+  int rcc = build_colouring(d, s, maps, nb, brick_cell, brick_geom);
+  if (rcc != B200MF_OK) return rcc;
   B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_brick_map, nb * L3 * sizeof(uint32_t)));
   B200MF_CUDA_CHECK(cudaMemcpy(s.d_brick_map, maps.data(), nb * L3 * sizeof(uint32_t),
                                cudaMemcpyHostToDevice));
@@ -167,7 +311,6 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
   s.brick_b = b;
   s.device_bytes += nb * L3 * sizeof(uint32_t);
   s.index_bytes += nb * L3 * sizeof(uint32_t);
-  maps.resize(nb * L3);
   if (s.n_geom != 1) return B200MF_OK; // the bulk kernel applies one cell shape per launch
   return build_bulk(d, s, maps, nb, true, bulk_stats);
 }

@@ -22,7 +22,7 @@
 namespace b200mf {
 
 namespace {
-constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, IDX = 0x3fffffffu;
+constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED, IDX = B200MF_BRICK_INDEX;
 constexpr int32_t FT_NONE = INT_MAX, FT_EARLY = -1;
 
 inline uint64_t hash_words(const uint32_t *w, size_t n, uint64_t h = 0x9e3779b97f4a7c15ull) {

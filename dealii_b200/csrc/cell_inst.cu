@@ -184,7 +184,7 @@ int debug_resolve_one(unsigned mask, int transpose, double *values_host) {
 template <int p, typename Number, bool DOT>
 int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                       uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
-                      bool overwrite, uint32_t geom) {
+                      bool overwrite, uint32_t geom, const uint32_t *list) {
   constexpr int b = brick_edge(p);
   using Cfg = BrickCfg<p, b, Number>;
   BrickKernelParams<p, Number> prm;
@@ -194,7 +194,8 @@ int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, cons
   prm.dst = static_cast<Number *>(dst);
   prm.dot_accum = dot_accum;
   prm.brick_begin = brick_begin;
-  prm.overwrite = overwrite ? 1 : 0;
+  prm.list = list;
+  prm.overwrite = list ? 2 : (overwrite ? 1 : 0);
   auto kernel = brick_cartesian_kernel<p, b, Number, DOT>;
   // (the attribute is per device: set it on every launch, it is a cheap driver call)
   B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -299,13 +300,14 @@ int B200MF_CAT(launch_bulk_n, B200MF_N)(const Setup &s, const b200mf_operator &o
 #if B200MF_N <= 9
 int B200MF_CAT(launch_bricks_n, B200MF_N)(const Setup &s, const b200mf_operator &op, void *dst,
                                           const void *src, uint64_t brick_begin, uint64_t n_bricks,
-                                          cudaStream_t st, double *dot, bool ow, uint32_t geom) {
+                                          cudaStream_t st, double *dot, bool ow, uint32_t geom,
+                                          const uint32_t *list) {
   constexpr int p = B200MF_N - 1;
   if (s.number == B200MF_F64)
-    return dot ? launch_bricks_one<p, double, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom)
-               : launch_bricks_one<p, double, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom);
-  return dot ? launch_bricks_one<p, float, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom)
-             : launch_bricks_one<p, float, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom);
+    return dot ? launch_bricks_one<p, double, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list)
+               : launch_bricks_one<p, double, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list);
+  return dot ? launch_bricks_one<p, float, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list)
+             : launch_bricks_one<p, float, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list);
 }
 #endif
 

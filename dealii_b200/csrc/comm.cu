@@ -397,8 +397,13 @@ static int dist_vmult_impl(const Setup &s, const b200mf_partitioner &p, const b2
   cudaStream_t cs = c->comm_stream;
   const uint64_t ni = s.n_cells_interior ? s.n_cells_interior : s.n_cells, nc = s.n_cells;
   const uint64_t W = s.n_bricks ? (uint64_t)s.brick_b * s.brick_b * s.brick_b : 1;
-  const uint64_t half = (ni / 2) / W * W; // pieces of a vmult never cut a brick
-  int rc = vmult_prepare_impl(s, op, dst, main);
+  const bool coloured = coloured_enabled(s, op);
+  const uint64_t half = coloured ? s.colouring.half : (ni / 2) / W * W; // pieces never cut a brick
+  auto piece = [&](int which, uint64_t cb, uint64_t ce) -> int {
+    return coloured ? launch_coloured(s, op, dst, src, which, main, dot_accum)
+                    : launch_cell_loop(s, op, dst, src, cb, ce, main, dot_accum, true);
+  };
+  int rc = coloured ? coloured_prepare(s, dst, main) : vmult_prepare_impl(s, op, dst, main);
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaEventRecord(c->ev[0], main));
   B200MF_CUDA_CHECK(cudaStreamWaitEvent(cs, c->ev[0], 0));
@@ -407,17 +412,17 @@ static int dist_vmult_impl(const Setup &s, const b200mf_partitioner &p, const b2
   rc = exchange(p, src, true, cs);
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaEventRecord(c->ev[1], cs));
-  rc = launch_cell_loop(s, op, dst, src, 0, half, main, dot_accum, true); // interior, part A
+  rc = piece(0, 0, half); // interior, part A
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaStreamWaitEvent(main, c->ev[1], 0));
-  rc = launch_cell_loop(s, op, dst, src, ni, nc, main, dot_accum, true); // cells touching ghosts
+  rc = piece(1, ni, nc); // cells touching ghosts
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaEventRecord(c->ev[2], main));
   B200MF_CUDA_CHECK(cudaStreamWaitEvent(cs, c->ev[2], 0));
   rc = exchange(p, dst, false, cs);
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaEventRecord(c->ev[3], cs));
-  rc = launch_cell_loop(s, op, dst, src, half, ni, main, dot_accum, true); // interior, part B
+  rc = piece(2, half, ni); // interior, part B
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaStreamWaitEvent(main, c->ev[3], 0));
   rc = b200mf_ghost_unpack_add(p.number, dst, p.d_buf, p.d_import_idx, p.n_import, main);

@@ -36,6 +36,10 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
   } while (0)
 
 constexpr int kMaxN = 9; // degree <= 8
+// flag bits of a brick map entry (bit 31 = B200MF_L2G_CONSTRAINED)
+constexpr uint32_t B200MF_BRICK_COMPLETE = 0x40000000u; // no cell outside the brick touches the dof
+constexpr uint32_t B200MF_BRICK_FIRST = 0x20000000u;    // coloured launches: this brick stores the dof
+constexpr uint32_t B200MF_BRICK_INDEX = 0x1fffffffu;
 constexpr int kL2gPadCells = 16; // >= cells per warp of every plane-kernel configuration
 // cells per direction of a brick: b^3 consecutive cells of a Morton-ordered mesh form a block;
 // chosen by measurement (Q1: b = 16 (L = 17) beats 8 by 20 % in FP64; Q3/Q4: b = 4 beats 2 by 20 %; Q5: b = 2 (L = 11, many small CTAs) beats
@@ -144,6 +148,21 @@ struct Setup {
   // without mask handling (plane kernel, sum-factorised diagonal) serve the cells outside
   uint64_t masked_begin = 0, masked_end = 0;
 
+  // coloured brick launches (brick_setup.cpp: build_colouring): no atomics, no memset of dst
+  struct Colouring {
+    bool ready = false, enabled = true;
+    int n_colours = 0;
+    uint64_t half = 0; // first half of the interior cells (piece 0 of the distributed schedule)
+    struct Launch { int piece; uint32_t geom; uint64_t offset, count; };
+    struct CellRange { int piece; uint64_t begin, end; };
+    std::vector<Launch> launches;   // in launch order: piece, cell shape, colour
+    std::vector<CellRange> general; // cells no brick covers, per piece
+    uint32_t *d_list = nullptr, *d_zero = nullptr;
+    uint64_t n_zero = 0;
+    float tuned_ms = 0.f;
+  };
+  mutable Colouring colouring;
+
   // bulk brick path (bulk_kernel.cuh / bulk_setup.cpp): pattern tables + per-brick descriptors in
   // execution order, first-toucher-stores write protocol
   struct Bulk {
@@ -211,7 +230,12 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload = true,
 // kernels: the bricks [brick_begin, brick_begin + n_bricks) of the setup
 int launch_bricks(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                   uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
-                  bool overwrite, uint32_t geom = 0);
+                  bool overwrite, uint32_t geom = 0, const uint32_t *list = nullptr);
+// the coloured launches and the per-cell kernels of one piece of the schedule (-1: all pieces)
+int launch_coloured(const Setup &s, const b200mf_operator &op, void *dst, const void *src, int piece,
+                    cudaStream_t stream, double *dot_accum);
+int coloured_prepare(const Setup &s, void *dst, cudaStream_t stream);
+bool coloured_enabled(const Setup &s, const b200mf_operator &op);
 
 // shape.cpp
 template <typename Number, int n>

@@ -207,6 +207,11 @@ class MatrixFree:
         returns whether the setup has bulk tables."""
         return bool(self._lib.b200mf_setup_enable_bulk(self._h, int(bool(enable))))
 
+    def select_brick_path(self, path):
+        """0 = index maps + memset + atomics, 1 = coloured launches, 2 = bulk tables; returns the
+        active path or -1 if the setup does not have the requested one."""
+        return int(self._lib.b200mf_setup_select_brick_path(self._h, int(path)))
+
     def bulk_info(self):
         info = L.BulkInfo()
         L.check(self._lib.b200mf_setup_get_bulk_info(self._h, C.byref(info)))

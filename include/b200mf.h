@@ -157,6 +157,12 @@ typedef struct {
    * measured for both (0 when the choice was forced with B200MF_BULK=0/1)                      */
   int enabled;
   double tuned_ms_index_map, tuned_ms_bulk;
+  /* the coloured launches (bricks of one colour share no dof: no atomics, first toucher stores: no
+   * memset; bit-reproducible), the third candidate of the setup-time measurement                */
+  double tuned_ms_coloured;
+  int n_colours, n_coloured_launches;
+  uint64_t n_zero_coloured;
+  int path; /* 0 = index maps + memset + atomics, 1 = coloured launches, 2 = bulk tables           */
 } b200mf_bulk_info;
 int b200mf_bulk_probe(const b200mf_setup_desc *desc, b200mf_bulk_info *info);
 /* The setup times both brick paths (index maps + memset + atomics vs bulk tables +
@@ -164,6 +170,9 @@ int b200mf_bulk_probe(const b200mf_setup_desc *desc, b200mf_bulk_info *info);
  * by measurement").  This switch overrides the choice (tests, A/B runs); returns whether bulk
  * tables exist.                                                                                  */
 int b200mf_setup_enable_bulk(b200mf_setup *s, int enable);
+/* path: 0 = index maps + memset + atomics, 1 = coloured launches, 2 = bulk tables; returns the path
+ * now active or -1 if the setup does not have it.                                                */
+int b200mf_setup_select_brick_path(b200mf_setup *s, int path);
 int b200mf_setup_get_bulk_info(const b200mf_setup *s, b200mf_bulk_info *info);
 
 /* Quadrature point coordinates, the input of PMF::evaluate_coefficients functors

@@ -50,16 +50,23 @@ def test_bulk_vmult_matches_oracle_per_entry(degree, extra, number):
     om, oracle, mf, op = make(degree, brick_refinements(degree) + extra, number)
     info = mf.bulk_info()
     assert info["usable"] == 1 and info["n_zero"] == 0 and info["n_general_cells"] == 0
-    mf.enable_bulk(True)                        # whatever the setup's own measurement chose
     src = np.random.default_rng(degree).random(om.n_dofs)
     x = torch.from_numpy(src.astype(mf.np_dtype)).cuda()
     y = mf.initialize_dof_vector()
     ref = oracle.vmult(src)
-    for rep in range(3):                        # repeated launches: flag epochs, ticket re-arming
-        y.fill_(float("nan"))                   # vmult must write every entry, no memset needed
-        op.vmult(y, x)
-        torch.cuda.synchronize()
-        assert_per_entry(y.cpu().numpy().astype(np.float64), ref, TOL[number])
+    # every brick path, whatever the setup's own measurement chose: 2 = bulk tables, 1 = coloured
+    # launches (both without a memset of dst), 0 = index maps + memset + atomics
+    for path in (2, 1, 0):
+        assert mf.select_brick_path(path) == path
+        results = []
+        for rep in range(3):                    # repeated launches: flag epochs, ticket re-arming
+            y.fill_(float("nan"))               # vmult must write every entry
+            op.vmult(y, x)
+            torch.cuda.synchronize()
+            results.append(y.clone())
+            assert_per_entry(y.cpu().numpy().astype(np.float64), ref, TOL[number])
+        if path == 1:                           # coloured launches are bit-reproducible
+            assert torch.equal(results[0], results[1]) and torch.equal(results[1], results[2])
 
 
 @pytest.mark.parametrize("degree,extra", [(4, 1), (3, 1), (2, 1), (6, 1)])
@@ -68,17 +75,18 @@ def test_bulk_helmholtz_dirichlet_both_constraint_semantics(degree, extra):
     for cpu_mf in (False, True):
         om, oracle, mf, op = make(degree, r, "f64", dirichlet=True, cpu_mf=cpu_mf, mass=10.0, grad=2.5)
         assert mf.bulk_info()["usable"] == 1
-        mf.enable_bulk(True)
         src = np.random.default_rng(3).random(om.n_dofs)
         if not cpu_mf:
             src[om.boundary_dofs] = 0.0
         x = torch.from_numpy(src).cuda()
         y = mf.initialize_dof_vector()
-        y.fill_(float("nan"))
-        op.vmult(y, x)
-        torch.cuda.synchronize()
         ref = oracle.vmult_cpu_matrixfree(src) if cpu_mf else oracle.vmult(src)
-        assert_per_entry(y.cpu().numpy(), ref, 1e-12)
+        for path in (2, 1):
+            assert mf.select_brick_path(path) == path
+            y.fill_(float("nan"))
+            op.vmult(y, x)
+            torch.cuda.synchronize()
+            assert_per_entry(y.cpu().numpy(), ref, 1e-12)
 
 
 @pytest.mark.parametrize("number", ["f64", "f32"])
@@ -114,12 +122,12 @@ def test_bulk_fused_dot_and_cg():
     inv_diag = op.compute_diagonal()
     b = torch.from_numpy(src).cuda()
     res = {}
-    for bulk in (True, False):
-        mf.enable_bulk(bulk)
+    for bulk in (2, 1, 0):
+        mf.select_brick_path(bulk)
         x = mf.initialize_dof_vector()
         solver = dealii_b200.SolverCG(dealii_b200.SolverControl(200, 1e-10 * float(np.linalg.norm(src))))
         r = solver.solve(op, x, b, inv_diag)
         res[bulk] = (r.iterations, x.clone())
-    mf.enable_bulk(True)
-    assert abs(res[True][0] - res[False][0]) <= 1
-    assert (res[True][1] - res[False][1]).abs().max().item() < 1e-8 * res[False][1].abs().max().item()
+    for path in (2, 1):
+        assert abs(res[path][0] - res[0][0]) <= 1
+        assert (res[path][1] - res[0][1]).abs().max().item() < 1e-8 * res[0][1].abs().max().item()

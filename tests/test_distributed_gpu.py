@@ -21,7 +21,7 @@ def _value(lat):
     return np.sin(0.37 * lat.astype(np.float64)) + 1.5
 
 
-def _run_rank(rank, world, port, dim, degree, refinements, amp, ret):
+def _run_rank(rank, world, port, dim, degree, refinements, amp, ret, path=None):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -31,6 +31,8 @@ def _run_rank(rank, world, port, dim, degree, refinements, amp, ret):
         pm = PartitionedHyperCubeMesh(dim, degree, refinements, world, rank, want_lattice_ids=True,
                                       dirichlet_boundary=True, deformation_amplitude=amp)
         dmf = DistributedMatrixFree(pm, "f64", dev)
+        if path is not None:
+            dmf.mf.select_brick_path(path)
         A = dealii_b200.LaplaceOperator(dmf.mf)
         src = dmf.initialize_dof_vector()
         src[:pm.n_owned] = torch.from_numpy(_value(pm.lattice_ids[:pm.n_owned])).to(dev)
@@ -68,17 +70,18 @@ def _reference(dim, degree, refinements, amp):
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-@pytest.mark.parametrize("dim,degree,refinements,amp", [(3, 4, 2, 0.0), (3, 2, 3, 0.05), (2, 3, 4, 0.0)])
-def test_distributed_vmult_and_cg(world, dim, degree, refinements, amp):
+@pytest.mark.parametrize("dim,degree,refinements,amp,path", [(3, 4, 2, 0.0, None), (3, 4, 3, 0.0, 1), (3, 4, 3, 0.0, 0),
+                                                             (3, 2, 3, 0.05, None), (2, 3, 4, 0.0, None)])
+def test_distributed_vmult_and_cg(world, dim, degree, refinements, amp, path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29600 + (os.getpid() % 2000)
     if world == 1:
         ret = {}
-        _run_rank(0, 1, port, dim, degree, refinements, amp, ret)
+        _run_rank(0, 1, port, dim, degree, refinements, amp, ret, path)
     else:
         ret = mp.Manager().dict()
-        mp.spawn(_run_rank, args=(world, port, dim, degree, refinements, amp, ret), nprocs=world, join=True)
+        mp.spawn(_run_rank, args=(world, port, dim, degree, refinements, amp, ret, path), nprocs=world, join=True)
     om, o, ref = _reference(dim, degree, refinements, amp)
     ref_diag = o.compute_diagonal()
     its = set()
@@ -109,7 +112,7 @@ def test_distributed_vmult_and_cg(world, dim, degree, refinements, amp):
 
 # ---------------------------------------------------------------------------------------------
 # BASELINE configs[3]: the adaptive (hanging-node) partitioned mesh through the distributed loop
-def _run_adaptive_rank(rank, world, port, degree, refinements, ret):
+def _run_adaptive_rank(rank, world, port, degree, refinements, ret, path=None):
     from dealii_b200.distributed import AdaptiveHyperCubeMesh
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
@@ -121,6 +124,8 @@ def _run_adaptive_rank(rank, world, port, degree, refinements, ret):
         mesh = AdaptiveHyperCubeMesh(3, degree, refinements, world, rank, coarse=coarse, ball_radius=0.33,
                                      want_coords=True)
         dmf = DistributedMatrixFree(mesh, "f64", dev)
+        if path is not None:
+            dmf.mf.select_brick_path(path)
         A = dealii_b200.LaplaceOperator(dmf.mf)
         n = mesh.n_owned
         cons = torch.from_numpy(mesh.constrained_dofs.astype(np.int64)).to(dev)     # hanging-node dofs
@@ -166,17 +171,18 @@ def _run_adaptive_rank(rank, world, port, degree, refinements, ret):
             dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_distributed_adaptive_mesh_properties(world):
+def test_distributed_adaptive_mesh_properties(world, path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29700 + (os.getpid() % 2000)
     if world == 1:
         ret = {}
-        _run_adaptive_rank(0, 1, port, 3, 4, ret)
+        _run_adaptive_rank(0, 1, port, 3, 4, ret, path)
     else:
         ret = mp.Manager().dict()
-        mp.spawn(_run_adaptive_rank, args=(world, port, 3, 4, ret), nprocs=world, join=True)
+        mp.spawn(_run_adaptive_rank, args=(world, port, 3, 4, ret, path), nprocs=world, join=True)
     defect, vau, uav, uau, n_global, n_masked, n_bricks = ret[0]
     assert n_masked > 0 and n_bricks > 0
     assert defect < 1e-11

@@ -13,8 +13,8 @@ def run(degree, refinements, number, reps=20):
     y = mf.initialize_dof_vector()
     out = dict(degree=degree, n_dofs=mf.n_owned, number=number, setup_s=round(setup_s, 2), bulk=mf.bulk_info())
     ref = None
-    for mode in ("bulk", "map"):
-        if not mf.enable_bulk(mode == "bulk"):
+    for mode, path in (("bulk", 2), ("coloured", 1), ("map", 0)):
+        if mf.select_brick_path(path) != path:
             continue
         for _ in range(3):
             op.vmult(y, x)
@@ -31,7 +31,6 @@ def run(degree, refinements, number, reps=20):
             ref = y.clone()
         else:
             out["maxdiff_rel"] = float((y - ref).abs().max() / ref.abs().max())
-    mf.enable_bulk(True)
     print(json.dumps(out), flush=True)
 
 if __name__ == "__main__":
