@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: BASELINE configs[1] (3D Q4 Laplace, Cartesian hyper_cube); c4: configs[3] (3D Q3 "
                          "Poisson, one refinement ball per cube = hanging nodes)")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE configs[4]: degrees 1-8, Cartesian and deformed (full-Jacobian) meshes, FP64 and "
+                         "FP32 vmult with the HBM-roofline fraction per case; one JSON line with a 'sweep' array")
     ap.add_argument("--ball-radius", type=float, default=0.35)
     ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--no-converged-cg", action="store_true")
@@ -600,6 +603,60 @@ def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
     return out
 
 
+def run_sweep(args):
+    """Degree sweep Q1-Q8, 3D, Cartesian (affine) and deformed (every cell general: full Jacobian,
+    MappingQ1 on displaced vertices) meshes, FP64 and FP32: vmult GDoF/s and fraction of the HBM
+    roofline with the algorithmic bytes of SURVEY.md 8(d) (2 s per dof + 6 s ((p+1)/p)^3 of merged
+    metric on general cells).  Clocks are sampled over the whole sweep."""
+    import torch
+    import dealii_b200
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(0)
+    peak, peak_src = measured_peak()
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.mark()
+    refinements = {1: 8, 2: 7, 3: 7, 4: 6, 5: 6, 6: 6, 7: 5, 8: 5}
+    rows = []
+    for degree in range(1, 9):
+        for amp in (0.0, 0.05):
+            mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements[degree], deformation_amplitude=amp)
+            for number in ("f64", "f32"):
+                mf = dealii_b200.MatrixFree(number).reinit_from_mesh(mesh)
+                op = dealii_b200.LaplaceOperator(mf)
+                x = torch.rand(mf.n_owned, dtype=mf.torch_dtype, device="cuda")
+                y = mf.initialize_dof_vector()
+                for _ in range(3):
+                    op.vmult(y, x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                e0.record()
+                for _ in range(reps):
+                    op.vmult(y, x)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                sz = 8 if number == "f64" else 4
+                bpd = 2 * sz + (6 * sz * ((degree + 1) / degree) ** 3 if amp else 0.0)
+                info = mf.bulk_info()
+                rows.append({"degree": degree, "number": number, "mesh": "deformed" if amp else "cartesian",
+                             "cell_kind": int(mf.info.cell_kind), "n_dofs": mf.n_owned, "ms_per_vmult": ms,
+                             "gdofs": mf.n_owned / ms / 1e6, "algorithmic_bytes_per_dof": bpd,
+                             "roofline_frac": bpd * mf.n_owned / (ms * 1e-3) / 1e9 / peak,
+                             "cells_in_bricks": int(mf.info.n_bricks * mf.info.cells_per_brick),
+                             "brick_path": info["path"] if mf.info.n_bricks else None})
+                del mf, op, x, y
+                torch.cuda.empty_cache()
+            del mesh
+    clocks = sampler.stop()
+    clocks["window"] = "the whole sweep"
+    return {"metric": "vmult_degree_sweep", "unit": UNIT, "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+            "peak": peak, "peak_source": peak_src, "clocks": clocks, "sweep": rows,
+            "config": {"workload": "3D Q1-Q8 Laplace vmult, Cartesian and deformed hyper_cube, f64 and f32 (BASELINE configs[4])",
+                       "l2": "vectors of 17-57 M dofs (>= L2 except f32 at 17 M: 68 MB)"}}
+
+
 class StdoutForJsonOnly:
     """Library banners (e.g. "NCCL version ..." printed by libnccl to fd 1) must not mix with the
     one JSON line of the contract: route fd 1 to stderr while the benchmark runs, restore it for
@@ -621,6 +678,6 @@ class StdoutForJsonOnly:
 if __name__ == "__main__":
     a = parse_args()
     with StdoutForJsonOnly() as guard:
-        line = run_reference(a) if a.impl == "reference" else run_engine(a)
+        line = run_reference(a) if a.impl == "reference" else (run_sweep(a) if a.sweep else run_engine(a))
     if line is not None:
         print(json.dumps(line), flush=True)

@@ -614,6 +614,18 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     return B200MF_ERR_CUDA;
   }
   b200mf_setup *h = new b200mf_setup();
+  // every early return below (B200MF_CUDA_CHECK / B200MF_REQUIRE / TRY) goes through this guard:
+  // it frees whatever the half-built setup already owns, incl. the temporaries d_qp / d_qw
+  double *d_qp = nullptr, *d_qw = nullptr;
+  struct Guard {
+    b200mf_setup *&h;
+    double *&qp, *&qw;
+    ~Guard() {
+      cudaFree(qp);
+      cudaFree(qw);
+      if (h) b200mf_setup_destroy(h);
+    }
+  } guard{h, d_qp, d_qw};
   Setup &s = h->impl;
   s.dim = d->dim; s.degree = d->degree; s.n = d->degree + 1; s.number = d->number;
   s.n_cells = d->n_cells; s.n_owned = d->n_owned_dofs; s.n_ghost = d->n_ghost_dofs;
@@ -622,7 +634,7 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   for (int i = 0; i < s.dim; ++i) s.dofs_per_cell *= s.n;
   const int n = s.n, nq = s.dofs_per_cell;
   int rc = B200MF_OK;
-#define TRY(x) do { rc = (x); if (rc != B200MF_OK) { b200mf_setup_destroy(h); return rc; } } while (0)
+#define TRY(x) do { rc = (x); if (rc != B200MF_OK) return rc; } while (0)
 
   // --- shape data
   build_fe_q_shape_data(s.degree, s.shape_values, s.shape_grad_colloc, s.q_weights,
@@ -693,7 +705,6 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   }
 
   // --- geometry
-  double *d_qp = nullptr, *d_qw = nullptr;
   TRY(dev_alloc_copy<double>(&d_qp, s.q_points_1d.data(), n, s, nullptr));
   TRY(dev_alloc_copy<double>(&d_qw, s.q_weights.data(), n, s, nullptr));
   const size_t NS = s.dim * (s.dim + 1) / 2;
@@ -773,12 +784,9 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     cudaFree(d_ij);
     cudaFree(d_jw);
   } else {
-    delete h;
     set_error("unknown geometry input kind %d", d->geometry);
     return B200MF_ERR_INVALID;
   }
-  cudaFree(d_qp);
-  cudaFree(d_qw);
   s.device_bytes += s.geometry_bytes;
   // "atomics or a colouring chosen by measurement" (north star; the reference offers graph
   // colouring or atomics, portable_matrix_free.templates.h:1060-1185): when the setup has both the
@@ -837,6 +845,7 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   B200MF_CUDA_CHECK(cudaGetLastError());
 #undef TRY
   *out = h;
+  h = nullptr; // released: the guard only frees the temporaries now
   return B200MF_OK;
 }
 
@@ -1064,7 +1073,11 @@ int b200mf_vmult_host(const b200mf_setup *h, const b200mf_operator *op, void *ds
   const size_t bytes = (s.n_owned + s.n_ghost) * number_size(s.number);
   for (int i = 0; i < 2; ++i)
     if (!s.d_stage[i]) B200MF_CUDA_CHECK(cudaMalloc(&s.d_stage[i], std::max<size_t>(bytes, 1)));
-  B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_stage[0], src_host, bytes, cudaMemcpyHostToDevice, 0));
+  // src_host / dst_host hold the n_owned locally owned entries (like the batch and CG entry points)
+  const size_t owned_bytes = s.n_owned * number_size(s.number);
+  B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_stage[0], src_host, owned_bytes, cudaMemcpyHostToDevice, 0));
+  if (bytes > owned_bytes)
+    B200MF_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(s.d_stage[0]) + owned_bytes, 0, bytes - owned_bytes, 0));
   int rc = b200mf_vmult(h, op, s.d_stage[1], s.d_stage[0], nullptr);
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaMemcpyAsync(dst_host, s.d_stage[1], s.n_owned * number_size(s.number),

@@ -16,6 +16,11 @@
  *     (matrix_free/portable_matrix_free.templates.h:296-298).
  * There is no CPU fallback: without a CUDA device every compute entry point fails with
  * B200MF_ERR_CUDA.
+ * Threading: a b200mf_setup owns per-setup scratch (solver work vectors, reduction slots, the
+ * staging buffers of the *_host entry points, the ticket/flag arrays of the bulk brick path), so
+ * the solver, *_host and vmult entry points of ONE setup must not run concurrently from several
+ * host threads or streams (Portable::MatrixFree::cell_loop is not re-entrant on one object either:
+ * it re-zeroes the ghost section of src).  Different setups are independent.
  */
 #ifndef B200MF_H
 #define B200MF_H
