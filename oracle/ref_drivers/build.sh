@@ -26,6 +26,16 @@ if [ ! -x "$BIN/ref_bench" ] || [ "$HERE/ref_bench.cc" -nt "$BIN/ref_bench" ]; t
   ( $CXX $FLAGS $INC "$HERE/ref_bench.cc" -o "$BIN/ref_bench" $LINK ) &
   pids+=($!)
 fi
+# the product-side deal.II adapter example (include/b200mf_dealii.hpp + examples/step64_dealii.cc):
+# deal.II host code driving libb200mf.so; it can only be compiled where deal.II's headers are
+ROOT="$HERE/../.."
+if [ -f "$ROOT/dealii_b200/libb200mf.so" ]; then
+  if [ ! -x "$BIN/step64_b200" ] || [ "$ROOT/examples/step64_dealii.cc" -nt "$BIN/step64_b200" ] || [ "$ROOT/include/b200mf_dealii.hpp" -nt "$BIN/step64_b200" ]; then
+    ( $CXX $FLAGS $INC -I"$ROOT/include" -I/usr/local/cuda/include "$ROOT/examples/step64_dealii.cc" -o "$BIN/step64_b200" \
+        $LINK -L"$ROOT/dealii_b200" -lb200mf -Wl,-rpath,\$ORIGIN/../../../dealii_b200 -L/usr/local/cuda/lib64 -lcudart ) &
+    pids+=($!)
+  fi
+fi
 rc=0
 for p in "${pids[@]:-}"; do [ -z "$p" ] || wait "$p" || rc=1; done
 exit $rc
