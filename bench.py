@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--no-converged-cg", action="store_true")
     ap.add_argument("--no-chebyshev", action="store_true")
+    ap.add_argument("--no-renumbered", action="store_true")
     ap.add_argument("--cg-rel-tol", type=float, default=1e-6)
     ap.add_argument("--cg-max-iterations", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -498,6 +499,13 @@ def run_engine(args):
         torch.cuda.empty_cache()
         cg = run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak)
 
+    # ---- the opt-in numbering DoFRenumbering::lexicographic (dofs/dof_renumbering.h:1327-1342): every
+    # brick's lattice is then an affine image of the numbering, the brick kernel computes its indices and
+    # streams no index map (strided bricks).  Reported beside the default numbering, never instead of it.
+    renumbered = None
+    if world == 1 and args.workload == "c2" and not args.deformation and not args.no_renumbered:
+        renumbered = run_renumbered(args, dev, peak)
+
     launches = lc1 - lc0
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -515,13 +523,77 @@ def run_engine(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.number, "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "cg": cg,
+                "roofline": roofline, "cpu_baseline": cpu, "cg": cg, "renumbered": renumbered,
                 "parity_check": parity["ok"], "parity": parity,
                 "e2e_matches_device": bool(check < 1e-12 if args.number == "f64" else check < 1e-5)}
     result = line if rank == 0 else None
     if world > 1:
         dist.destroy_process_group()
     return result
+
+
+def run_renumbered(args, dev, peak):
+    """The same workload on the DoFHandler renumbered with DoFRenumbering::lexicographic: vmult, the
+    cell-loop kernel alone, and CG + Jacobi (fixed iteration count)."""
+    import torch
+    import dealii_b200
+    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements, numbering="lexicographic")
+    mf = dealii_b200.MatrixFree(args.number, dev).reinit_from_mesh(mesh)
+    op = dealii_b200.LaplaceOperator(mf)
+    info = mf.bulk_info()
+    n = mf.n_owned
+    x = torch.rand(n, dtype=mf.torch_dtype, device=dev)
+    y = mf.initialize_dof_vector()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(f, reps):
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    reps = max(args.steps, 10)
+    ms = timed(lambda: op.vmult(y, x), reps)
+    ms_k = timed(lambda: mf.vmult_range(op.op, y, x, 0, mesh.n_cells), reps)
+    bpd = BYTES_PER_DOF[args.number]
+    out = {"numbering": "DoFRenumbering::lexicographic (opt-in; bit-identical to the reference's function, tests/test_mesh.py)",
+           "strided_bricks": bool(info["strided"]), "brick_path": info["path"],
+           "value": n / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "kernel_ms": ms_k,
+           "roofline_frac_kernel": bpd * n / (ms_k * 1e-3) / 1e9 / peak,
+           "roofline_frac_vmult": bpd * n / (ms * 1e-3) / 1e9 / peak,
+           "traffic": "profiles/r02_brick_strided_q4_f64_ncu.txt: 1.92 GB read + 1.06 GB written per launch"}
+    del x, y
+    if not args.no_cg:
+        mesh_d = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements, numbering="lexicographic",
+                                           dirichlet_boundary=True)
+        mfd = dealii_b200.MatrixFree(args.number, dev).reinit_from_mesh(mesh_d)
+        A = dealii_b200.LaplaceOperator(mfd)
+        inv = A.compute_diagonal()
+        b = torch.ones(mfd.n_owned, dtype=mfd.torch_dtype, device=dev)
+        mfd.set_constrained_values(0.0, b)
+        iters = max(min(args.steps, 30), 10)
+        best = None
+        for rep in range(2):
+            xs = mfd.initialize_dof_vector()
+            control = dealii_b200.SolverControl(iters, 1e-300)
+            e0.record()
+            try:
+                dealii_b200.SolverCG(control).solve(A, xs, b, inv)
+            except dealii_b200.B200MFError:
+                pass
+            e1.record()
+            torch.cuda.synchronize()
+            best = e0.elapsed_time(e1)
+        its = control.last_step()
+        out["cg"] = {"value": mfd.n_owned * its / (best * 1e-3) / 1e9, "unit": "GDoF-iterations/s", "iterations": its,
+                     "ms_per_iteration": best / max(its, 1),
+                     "roofline_frac": CG_BYTES_PER_DOF[args.number] * mfd.n_owned * its / (best * 1e-3) / 1e9 / peak}
+    return out
 
 
 def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):

@@ -47,7 +47,7 @@ class BulkInfo(C.Structure):
                 ("usable", C.c_int), ("enabled", C.c_int),
                 ("tuned_ms_index_map", C.c_double), ("tuned_ms_bulk", C.c_double),
                 ("tuned_ms_coloured", C.c_double), ("n_colours", C.c_int), ("n_coloured_launches", C.c_int),
-                ("n_zero_coloured", u64), ("path", C.c_int)]
+                ("n_zero_coloured", u64), ("path", C.c_int), ("strided", C.c_int)]
 
 
 class Operator(C.Structure):
@@ -81,7 +81,7 @@ class MeshDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("cells_per_direction", C.c_int),
                 ("cell_order", C.c_int), ("left", C.c_double), ("right", C.c_double),
                 ("deformation", C.c_int), ("deformation_amplitude", C.c_double),
-                ("dirichlet_boundary", C.c_int), ("mark_constrained_l2g", C.c_int)]
+                ("dirichlet_boundary", C.c_int), ("mark_constrained_l2g", C.c_int), ("dof_numbering", C.c_int)]
 
 
 class PartitionDesc(C.Structure):
@@ -173,6 +173,7 @@ SYMBOLS = {
     "b200mf_bulk_probe": (C.c_int, [C.POINTER(SetupDesc), C.POINTER(BulkInfo)]),
     "b200mf_setup_enable_bulk": (C.c_int, [vp, C.c_int]),
     "b200mf_setup_select_brick_path": (C.c_int, [vp, C.c_int]),
+    "b200mf_setup_enable_strided": (C.c_int, [vp, C.c_int]),
     "b200mf_setup_get_bulk_info": (C.c_int, [vp, C.POINTER(BulkInfo)]),
     "b200mf_vmult_prepare": (C.c_int, [vp, C.POINTER(Operator), vp, vp]),
     "b200mf_vmult_range": (C.c_int, [vp, C.POINTER(Operator), vp, vp, u64, u64, vp, vp]),

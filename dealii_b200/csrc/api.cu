@@ -856,7 +856,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
   cudaFree(s->d_diag_tables);
   cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map); cudaFree(s->d_zero_list);
-  cudaFree(s->colouring.d_list); cudaFree(s->colouring.d_zero);
+  cudaFree(s->colouring.d_list); cudaFree(s->colouring.d_zero); cudaFree(s->d_brick_strided);
   free_bulk(*s);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
   for (void *w : s->d_work) cudaFree(w);
@@ -991,6 +991,12 @@ int b200mf_setup_enable_bulk(b200mf_setup *h, int enable) {
   return h->impl.bulk.ready ? 1 : 0;
 }
 
+int b200mf_setup_enable_strided(b200mf_setup *h, int enable) {
+  B200MF_REQUIRE(h, "null argument");
+  h->impl.strided_enabled = enable != 0;
+  return h->impl.d_brick_strided != nullptr ? 1 : 0;
+}
+
 int b200mf_setup_select_brick_path(b200mf_setup *h, int path) {
   B200MF_REQUIRE(h && path >= 0 && path <= 2, "bad argument");
   Setup &s = h->impl;
@@ -1014,6 +1020,7 @@ int b200mf_setup_get_bulk_info(const b200mf_setup *h, b200mf_bulk_info *info) {
   info->n_colours = h->impl.colouring.ready ? h->impl.colouring.n_colours : 0;
   info->n_coloured_launches = (int)h->impl.colouring.launches.size();
   info->n_zero_coloured = h->impl.colouring.n_zero;
+  info->strided = (h->impl.d_brick_strided != nullptr && h->impl.strided_enabled) ? 1 : 0;
   info->path = (h->impl.bulk.ready && h->impl.bulk.enabled) ? 2 : ((h->impl.colouring.ready && h->impl.colouring.enabled) ? 1 : 0);
   return B200MF_OK;
 }

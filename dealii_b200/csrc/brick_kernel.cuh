@@ -117,12 +117,24 @@ struct BrickKernelParams {
   double *dot_accum; // optional: += src . (A src) over these bricks
   unsigned long long brick_begin;
   const uint32_t *list; // optional: brick ids of this launch (coloured launches)
+  // STRIDED kernels: per brick {base, stride_y, stride_z, flags}: the lattice is an affine image of the
+  // numbering (index = base + x + stride_y y + stride_z z, e.g. after DoFRenumbering::lexicographic), so
+  // no index map is read; flags: bit f = lattice face f (x-,x+,y-,y+,z-,z+) is shared with cells outside
+  // the brick, bit 6+f = the dofs of face f are constrained
+  const uint4 *strided;
   // 0: add into dst; 1: dst is known to be zero (vmult) -> complete dofs are stored, the others use
   // RED; 2: coloured launch: complete / first-toucher dofs are stored, the others load-add-store
   int overwrite;
 };
 
-template <int p, int b, typename Number, bool DOT>
+// lattice face flags of a node
+template <int L>
+__device__ __forceinline__ bool on_flagged_face(uint32_t bits, int x, int y, int z) {
+  return ((bits & 1u) && x == 0) || ((bits & 2u) && x == L - 1) || ((bits & 4u) && y == 0) ||
+         ((bits & 8u) && y == L - 1) || ((bits & 16u) && z == 0) || ((bits & 32u) && z == L - 1);
+}
+
+template <int p, int b, typename Number, bool DOT, bool STRIDED>
 // (the register bound is only needed by the DOT variant; without it ptxas picks 64 registers for
 // the plain one, which measures 4 % faster than the 96 it takes when allowed to)
 __global__ void __launch_bounds__(BrickCfg<p, b, Number>::threads, DOT ? BrickCfg<p, b, Number>::ctas_per_sm : 0)
@@ -138,9 +150,28 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
                                             : prm.brick_begin + blockIdx.x;
   const uint32_t *__restrict__ map = prm.map + brick * (unsigned long long)L3;
   const Number *__restrict__ src = prm.src;
+  uint4 sd = make_uint4(0u, 0u, 0u, 0u);
+  if (STRIDED) sd = __ldg(prm.strided + brick);
 
   // ---- read_dof_values of the whole brick: every lattice node once
-  {
+  if (STRIDED) {
+    // computed indices: thread <-> (x, y) walks its z column, consecutive lanes read consecutive dofs
+    // of a lattice x-line; one multiply-add per node, no index map
+    if (tid < L2) {
+      const int gx = tid % L, gy = tid / L;
+      const uint32_t line = sd.x + gx + sd.y * gy;
+      const uint32_t cbits = sd.w >> 6;
+      const bool cons_xy = cbits != 0u && on_flagged_face<L>(cbits & 15u, gx, gy, 1);
+      Number val[L];
+#pragma unroll
+      for (int z = 0; z < L; ++z) {
+        const bool cons = cons_xy || ((cbits & 16u) && z == 0) || ((cbits & 32u) && z == L - 1);
+        val[z] = cons ? Number(0) : __ldg(src + line + sd.z * z);
+      }
+#pragma unroll
+      for (int z = 0; z < L; ++z) P0[tid + z * L2] = val[z];
+    }
+  } else {
     uint32_t idx[Cfg::gather_iters];
 #pragma unroll
     for (int k = 0; k < Cfg::gather_iters; ++k) {
@@ -196,17 +227,33 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
 
   // the indices of this thread's z line (the scatter targets): requested now, used after the
   // y sweep, so the z sweep never waits for them
-  uint32_t mz[L];
-  if (active) {
+  uint32_t mz[STRIDED ? 1 : L];
+  // strided mode: the word of node z of this thread's line is computed where it is used (z is a
+  // compile-time constant there)
+  uint32_t s_line = 0u, s_shared_xy = 0u, s_cons_xy = 0u;
+  if (STRIDED) {
+    s_line = sd.x + la + sd.y * lb; // la = x, lb = y of this thread's z line
+    s_shared_xy = on_flagged_face<L>(sd.w & 15u, la, lb, 1) ? 1u : 0u;
+    s_cons_xy = ((sd.w >> 6) != 0u && on_flagged_face<L>((sd.w >> 6) & 15u, la, lb, 1)) ? 1u : 0u;
+  }
+  auto word = [&](int z) -> uint32_t {
+    if (STRIDED) {
+      const bool shared = s_shared_xy || ((sd.w & 16u) && z == 0) || ((sd.w & 32u) && z == L - 1);
+      const bool cons = s_cons_xy || ((sd.w & (16u << 6)) && z == 0) || ((sd.w & (32u << 6)) && z == L - 1);
+      return (s_line + sd.z * z) | (shared ? 0u : B200MF_MAP_COMPLETE) | (cons ? CBIT : 0u);
+    }
+    return mz[STRIDED ? 0 : z];
+  };
+  if (active && !STRIDED) {
 #pragma unroll
-    for (int z = 0; z < L; ++z) mz[z] = __ldg(map + tid + z * L2);
+    for (int z = 0; z < L; ++z) mz[STRIDED ? 0 : z] = __ldg(map + tid + z * L2);
     if (prm.overwrite == 2) {
       // coloured launch: the dofs an earlier launch stored are read back at scatter time; ask L2
       // for them now so that the reads do not sit on the critical path of the z sweep
 #pragma unroll
       for (int z = 0; z < L; ++z)
-        if ((mz[z] & (CBIT | B200MF_MAP_COMPLETE | B200MF_MAP_FIRST)) == 0)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.dst + (mz[z] & B200MF_MAP_INDEX)));
+        if ((word(z) & (CBIT | B200MF_MAP_COMPLETE | B200MF_MAP_FIRST)) == 0)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.dst + (word(z) & B200MF_MAP_INDEX)));
     }
   }
 
@@ -273,7 +320,7 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
       if (DOT) {
 #pragma unroll
         for (int k = 0; k < p; ++k)
-          ui[k] = (mz[c * p + k] & CBIT) ? Number(0) : __ldg(src + (mz[c * p + k] & B200MF_MAP_INDEX));
+          ui[k] = (word(c * p + k) & CBIT) ? Number(0) : __ldg(src + (word(c * p + k) & B200MF_MAP_INDEX));
       }
       // values already in dst that this brick adds to, requested before the block's arithmetic:
       // cell_loop mode adds into the complete dofs (the others go through RED), a coloured launch
@@ -283,7 +330,7 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
         const uint32_t bits = prm.overwrite == 2 ? (CBIT | B200MF_MAP_COMPLETE | B200MF_MAP_FIRST) : (CBIT | B200MF_MAP_COMPLETE);
 #pragma unroll
         for (int k = 0; k < p; ++k)
-          old[k] = (mz[c * p + k] & bits) == want ? dst[mz[c * p + k] & B200MF_MAP_INDEX] : Number(0);
+          old[k] = (word(c * p + k) & bits) == want ? dst[word(c * p + k) & B200MF_MAP_INDEX] : Number(0);
       }
 #pragma unroll
       for (int k = 1; k < n; ++k) {
@@ -301,13 +348,13 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
       if (c > 0) oV[0] += cV;
 #pragma unroll
       for (int k = 0; k < p; ++k)
-        emit(mz[c * p + k], oV[k], DOT ? ui[k] : Number(0), prm.overwrite == 1 ? Number(0) : old[k]);
+        emit(word(c * p + k), oV[k], DOT ? ui[k] : Number(0), prm.overwrite == 1 ? Number(0) : old[k]);
       cV = oV[p];
       inC[0] = inC[p];
       inD[0] = inD[p];
     }
     {
-      const uint32_t m = mz[L - 1];
+      const uint32_t m = word(L - 1);
       Number u = Number(0);
       if (DOT && !(m & CBIT)) u = __ldg(src + (m & B200MF_MAP_INDEX));
       Number o = Number(0);

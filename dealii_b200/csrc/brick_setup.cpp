@@ -302,7 +302,70 @@ int build_bricks(const b200mf_setup_desc &d, Setup &s, bool upload, uint64_t *n_
     }
   }
   maps.resize(nb * L3);
-  int rcc = build_colouring(d, s, maps, nb, brick_cell, brick_geom);
+  // ---- strided bricks: index = base + x + sy y + sz z for every node, flags constant per lattice
+  // face (what DoFRenumbering::lexicographic, include/deal.II/dofs/dof_renumbering.h:1327-1342, produces
+  // on a tensor-product mesh): then no map has to be streamed at all
+  {
+    std::vector<uint4> desc(nb);
+    bool all = std::getenv("B200MF_NO_STRIDED") == nullptr;
+#pragma omp parallel for schedule(static)
+    for (int64_t w = 0; w < (int64_t)nb; ++w) {
+      if (!all) continue;
+      const uint32_t *m = maps.data() + (uint64_t)w * L3;
+      // reference node: the lattice centre is never constrained by a face flag... any unconstrained node
+      bool ok = true;
+      // face flags from the face centres' neighbours: derive per face from all its nodes
+      uint32_t shared = 0, cons = 0;
+      auto face_of = [&](int X, int Y, int Z, int f) {
+        switch (f) { case 0: return X == 0; case 1: return X == L - 1; case 2: return Y == 0; case 3: return Y == L - 1;
+                     case 4: return Z == 0; default: return Z == L - 1; }
+      };
+      // a face is constrained / shared if its centre node is
+      for (int f = 0; f < 6; ++f) {
+        int X = L / 2, Y = L / 2, Z = L / 2;
+        if (f == 0) X = 0; if (f == 1) X = L - 1; if (f == 2) Y = 0; if (f == 3) Y = L - 1; if (f == 4) Z = 0; if (f == 5) Z = L - 1;
+        const uint32_t v = m[X + L * (Y + L * Z)];
+        if (v & CBIT) cons |= 1u << f;
+        else if (!(v & COMPLETE)) shared |= 1u << f;
+      }
+      // strides from an interior node and its neighbours (interior nodes are never constrained here)
+      const int c0 = 1 + L * (1 + L * 1);
+      if ((m[c0] | m[c0 + 1] | m[c0 + L] | m[c0 + L2]) & CBIT) ok = false;
+      uint32_t sx = 0, sy = 0, sz = 0, base = 0;
+      if (ok) {
+        const uint32_t i0 = m[c0] & B200MF_BRICK_INDEX;
+        sx = (m[c0 + 1] & B200MF_BRICK_INDEX) - i0;
+        sy = (m[c0 + L] & B200MF_BRICK_INDEX) - i0;
+        sz = (m[c0 + L2] & B200MF_BRICK_INDEX) - i0;
+        base = i0 - sx - sy - sz;
+        if (sx != 1 || (int32_t)sy <= 0 || (int32_t)sz <= 0) ok = false;
+      }
+      for (int Z = 0; Z < L && ok; ++Z)
+        for (int Y = 0; Y < L && ok; ++Y)
+          for (int X = 0; X < L; ++X) {
+            const uint32_t v = m[X + L * (Y + L * Z)];
+            bool want_cons = false, want_shared = false;
+            for (int f = 0; f < 6; ++f)
+              if (face_of(X, Y, Z, f)) { want_cons |= (cons >> f) & 1u; want_shared |= (shared >> f) & 1u; }
+            if (want_cons) { if (!(v & CBIT)) { ok = false; break; } continue; }
+            if (v & CBIT) { ok = false; break; }
+            if ((v & B200MF_BRICK_INDEX) != base + X + sy * Y + sz * Z) { ok = false; break; }
+            if (((v & COMPLETE) != 0) == want_shared) { ok = false; break; }
+          }
+      if (!ok) {
+#pragma omp atomic write
+        all = false;
+      }
+      desc[w] = make_uint4(base, sy, sz, shared | (cons << 6));
+    }
+    if (all && nb > 0) {
+      B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_brick_strided, nb * sizeof(uint4)));
+      B200MF_CUDA_CHECK(cudaMemcpy(s.d_brick_strided, desc.data(), nb * sizeof(uint4), cudaMemcpyHostToDevice));
+      s.device_bytes += nb * sizeof(uint4);
+      s.index_bytes += nb * sizeof(uint4);
+    }
+  }
+  int rcc = s.d_brick_strided ? B200MF_OK : build_colouring(d, s, maps, nb, brick_cell, brick_geom);
   if (rcc != B200MF_OK) return rcc;
   B200MF_CUDA_CHECK(cudaMalloc((void **)&s.d_brick_map, nb * L3 * sizeof(uint32_t)));
   B200MF_CUDA_CHECK(cudaMemcpy(s.d_brick_map, maps.data(), nb * L3 * sizeof(uint32_t),

@@ -181,7 +181,7 @@ int debug_resolve_one(unsigned mask, int transpose, double *values_host) {
   return B200MF_OK;
 }
 
-template <int p, typename Number, bool DOT>
+template <int p, typename Number, bool DOT, bool STRIDED>
 int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                       uint64_t brick_begin, uint64_t n_bricks, cudaStream_t stream, double *dot_accum,
                       bool overwrite, uint32_t geom, const uint32_t *list) {
@@ -196,7 +196,8 @@ int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, cons
   prm.brick_begin = brick_begin;
   prm.list = list;
   prm.overwrite = list ? 2 : (overwrite ? 1 : 0);
-  auto kernel = brick_cartesian_kernel<p, b, Number, DOT>;
+  prm.strided = STRIDED ? s.d_brick_strided : nullptr;
+  auto kernel = brick_cartesian_kernel<p, b, Number, DOT, STRIDED>;
   // (the attribute is per device: set it on every launch, it is a cheap driver call)
   B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::smem_bytes));
@@ -300,14 +301,16 @@ int B200MF_CAT(launch_bulk_n, B200MF_N)(const Setup &s, const b200mf_operator &o
 #if B200MF_N <= 9
 int B200MF_CAT(launch_bricks_n, B200MF_N)(const Setup &s, const b200mf_operator &op, void *dst,
                                           const void *src, uint64_t brick_begin, uint64_t n_bricks,
-                                          cudaStream_t st, double *dot, bool ow, uint32_t geom,
+                                          cudaStream_t st__, double *dot, bool ow, uint32_t geom,
                                           const uint32_t *list) {
   constexpr int p = B200MF_N - 1;
-  if (s.number == B200MF_F64)
-    return dot ? launch_bricks_one<p, double, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list)
-               : launch_bricks_one<p, double, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list);
-  return dot ? launch_bricks_one<p, float, true>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list)
-             : launch_bricks_one<p, float, false>(s, op, dst, src, brick_begin, n_bricks, st, dot, ow, geom, list);
+  const bool st = s.d_brick_strided != nullptr && s.strided_enabled && list == nullptr;
+#define B200MF_LB(T, D) (st ? launch_bricks_one<p, T, D, true>(s, op, dst, src, brick_begin, n_bricks, st_, dot, ow, geom, list) \
+                            : launch_bricks_one<p, T, D, false>(s, op, dst, src, brick_begin, n_bricks, st_, dot, ow, geom, list))
+  cudaStream_t st_ = st__;
+  if (s.number == B200MF_F64) return dot ? B200MF_LB(double, true) : B200MF_LB(double, false);
+  return dot ? B200MF_LB(float, true) : B200MF_LB(float, false);
+#undef B200MF_LB
 }
 #endif
 

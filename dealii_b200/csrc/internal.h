@@ -135,6 +135,10 @@ struct Setup {
   struct BrickRun { uint64_t cell_begin, cell_end, first_brick; uint32_t geom; };
   uint32_t *d_brick_map = nullptr;
   uint64_t n_bricks = 0;
+  // every brick's lattice is an affine image of the numbering (index = base + x + sy y + sz z):
+  // {base, sy, sz, face flags} per brick, the kernels compute indices instead of reading the map
+  uint4 *d_brick_strided = nullptr;
+  bool strided_enabled = true;
   // dofs vmult has to zero before its cell loop (all that no brick stores); valid if have_zero_list
   uint32_t *d_zero_list = nullptr;
   uint64_t n_zero_list = 0;

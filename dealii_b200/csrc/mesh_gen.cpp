@@ -113,6 +113,14 @@ int b200mf_mesh_create(const b200mf_mesh_desc *d, b200mf_mesh **out) {
     }
   }
   m->n_dofs = (uint64_t)next;
+  if (d->dof_numbering == 1) {
+    // DoFRenumbering::lexicographic: support points sorted by the last coordinate first, i.e. the new
+    // number of a dof is its rank in the lattice order x fastest (every lattice point of a uniformly
+    // refined cube carries a dof)
+    int32_t r = 0;
+    for (uint64_t idx = 0; idx < lattice_size; ++idx)
+      if (lattice[idx] >= 0) lattice[idx] = r++;
+  }
   // boundary dofs
   std::vector<uint8_t> is_boundary;
   if (d->dirichlet_boundary) {

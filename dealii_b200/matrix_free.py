@@ -38,7 +38,8 @@ class HyperCubeMesh:
     GridGenerator::hyper_cube + refine_global + DoFHandler::distribute_dofs."""
 
     def __init__(self, dim, degree, refinements=None, subdivisions=None, left=0.0, right=1.0,
-                 deformation_amplitude=0.0, dirichlet_boundary=False, mark_constrained_l2g=False):
+                 deformation_amplitude=0.0, dirichlet_boundary=False, mark_constrained_l2g=False,
+                 numbering="default"):
         lib = L.load()
         d = L.MeshDesc()
         d.dim, d.degree = dim, degree
@@ -51,6 +52,7 @@ class HyperCubeMesh:
         d.deformation_amplitude = deformation_amplitude
         d.dirichlet_boundary = int(dirichlet_boundary)
         d.mark_constrained_l2g = int(mark_constrained_l2g)
+        d.dof_numbering = 1 if numbering == "lexicographic" else 0   # DoFRenumbering::lexicographic
         self._h = C.c_void_p()
         L.check(lib.b200mf_mesh_create(C.byref(d), C.byref(self._h)))
         v = L.MeshView()
@@ -206,6 +208,10 @@ class MatrixFree:
         """A/B switch between the bulk brick tables and the per-node index maps (tests, bench);
         returns whether the setup has bulk tables."""
         return bool(self._lib.b200mf_setup_enable_bulk(self._h, int(bool(enable))))
+
+    def enable_strided(self, enable=True):
+        """A/B switch for the computed-index bricks; returns whether the setup has them."""
+        return bool(self._lib.b200mf_setup_enable_strided(self._h, int(bool(enable))))
 
     def select_brick_path(self, path):
         """0 = index maps + memset + atomics, 1 = coloured launches, 2 = bulk tables; returns the

@@ -168,6 +168,10 @@ typedef struct {
   int n_colours, n_coloured_launches;
   uint64_t n_zero_coloured;
   int path; /* 0 = index maps + memset + atomics, 1 = coloured launches, 2 = bulk tables           */
+  /* 1: every brick's lattice is an affine image of the numbering (index = base + x + sy y + sz z, e.g.
+   * after DoFRenumbering::lexicographic, dofs/dof_renumbering.h:1327-1342): path 0 computes the indices
+   * and streams no index map                                                                       */
+  int strided;
 } b200mf_bulk_info;
 int b200mf_bulk_probe(const b200mf_setup_desc *desc, b200mf_bulk_info *info);
 /* The setup times both brick paths (index maps + memset + atomics vs bulk tables +
@@ -178,6 +182,8 @@ int b200mf_setup_enable_bulk(b200mf_setup *s, int enable);
 /* path: 0 = index maps + memset + atomics, 1 = coloured launches, 2 = bulk tables; returns the path
  * now active or -1 if the setup does not have it.                                                */
 int b200mf_setup_select_brick_path(b200mf_setup *s, int path);
+/* A/B switch for the computed-index (strided) bricks; returns whether the setup has them.            */
+int b200mf_setup_enable_strided(b200mf_setup *s, int enable);
 int b200mf_setup_get_bulk_info(const b200mf_setup *s, b200mf_bulk_info *info);
 
 /* Quadrature point coordinates, the input of PMF::evaluate_coefficients functors
@@ -441,6 +447,10 @@ typedef struct {
   double deformation_amplitude;
   int dirichlet_boundary;   /* 1 => collect boundary dofs as constrained                 */
   int mark_constrained_l2g; /* 1 => set B200MF_L2G_CONSTRAINED bits (CPU-MF semantics)   */
+  /* 0: DoFHandler::distribute_dofs numbering (first touch); 1: that numbering followed by
+   * DoFRenumbering::lexicographic (dofs/dof_renumbering.h:1327-1342; source/dofs/dof_renumbering.cc:
+   * 2636-2684: support points sorted by z, then y, then x) -- b200mf_mesh_create only           */
+  int dof_numbering;
 } b200mf_mesh_desc;
 
 typedef struct {

@@ -15,12 +15,14 @@
 //   (grad v, grad u) + (v, a u)   with a = 0 (Laplace), a = 10, or a = 10 / (0.05 + 2 |x|^2).
 //
 // usage: ref_dump <dim> <degree> <refinements> <mesh: cartesian|deformed|hanging|ball>
-//                 <op: laplace|helmholtz|helmholtz_var> <dirichlet: 0|1> <outdir>
+//                 <op: laplace|helmholtz|helmholtz_var> <dirichlet: 0|1> <outdir> [lexicographic]
+// (lexicographic: DoFRenumbering::lexicographic after distribute_dofs)
 // Compiled once per degree (-DREF_DEGREE=k).  Output: raw little-endian arrays + manifest.json.
 #include <deal.II/base/function.h>
 #include <deal.II/base/quadrature_lib.h>
 
 #include <deal.II/dofs/dof_handler.h>
+#include <deal.II/dofs/dof_renumbering.h>
 #include <deal.II/dofs/dof_tools.h>
 
 #include <deal.II/fe/fe_q.h>
@@ -257,7 +259,7 @@ private:
 template <int dim, int degree>
 int
 run(const unsigned int refinements, const std::string &mesh, const std::string &op,
-    const bool dirichlet, const std::string &outdir)
+    const bool dirichlet, const std::string &outdir, const bool lexicographic)
 {
   Triangulation<dim> tria;
   GridGenerator::hyper_cube(tria, 0., 1.);
@@ -296,6 +298,8 @@ run(const unsigned int refinements, const std::string &mesh, const std::string &
   const QGauss<1>  quad(degree + 1);
   DoFHandler<dim>  dof(tria);
   dof.distribute_dofs(fe);
+  if (lexicographic)
+    DoFRenumbering::lexicographic(dof); // dofs/dof_renumbering.h:1327-1342
   const unsigned int n_dofs = dof.n_dofs();
 
   AffineConstraints<double> constraints;
@@ -518,7 +522,7 @@ run(const unsigned int refinements, const std::string &mesh, const std::string &
 int
 main(int argc, char **argv)
 {
-  if (argc != 8)
+  if (argc != 8 && argc != 9)
     {
       std::fprintf(stderr, "usage: %s dim degree refinements mesh op dirichlet outdir\n", argv[0]);
       return 1;
@@ -530,15 +534,16 @@ main(int argc, char **argv)
     const unsigned int refinements = std::atoi(argv[3]);
     const std::string  mesh = argv[4], op = argv[5], outdir = argv[7];
     const bool         dirichlet = std::atoi(argv[6]) != 0;
+    const bool         lexicographic = argc == 9 && std::string(argv[8]) == "lexicographic";
     if (degree != REF_DEGREE)
       {
         std::fprintf(stderr, "this binary was compiled for degree %d\n", REF_DEGREE);
         rc = 1;
       }
     else if (dim == 2)
-      rc = run<2, REF_DEGREE>(refinements, mesh, op, dirichlet, outdir);
+      rc = run<2, REF_DEGREE>(refinements, mesh, op, dirichlet, outdir, lexicographic);
     else
-      rc = run<3, REF_DEGREE>(refinements, mesh, op, dirichlet, outdir);
+      rc = run<3, REF_DEGREE>(refinements, mesh, op, dirichlet, outdir, lexicographic);
   }
   Kokkos::finalize();
   return rc;

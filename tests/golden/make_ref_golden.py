@@ -45,6 +45,9 @@ CASES = {
     "c5_q2_deformed": (3, 2, 2, "deformed", "laplace", 0, True),
     "c5_q4_deformed": (3, 4, 2, "deformed", "laplace", 0, False),
     "c5_q3_deformed_helmholtz": (3, 3, 2, "deformed", "helmholtz_var", 1, False),
+    # opt-in numbering DoFRenumbering::lexicographic (the strided brick path)
+    "lex_q4": (3, 4, 2, "cartesian", "laplace", 1, False, "lexicographic"),
+    "lex_q2": (3, 2, 3, "cartesian", "helmholtz", 0, False, "lexicographic"),
     # 2D
     "d2_q2_hanging": (2, 2, 3, "hanging", "helmholtz_var", 1, True),
     "d2_q4_cartesian": (2, 4, 3, "cartesian", "laplace", 1, False),
@@ -52,10 +55,11 @@ CASES = {
 
 
 def run_case(name, spec):
-    dim, degree, ref, mesh, op, dirichlet, keep_jac = spec
+    dim, degree, ref, mesh, op, dirichlet, keep_jac = spec[:7]
+    extra = list(spec[7:])
     exe = os.path.join(BIN, f"ref_dump_q{degree}")
     with tempfile.TemporaryDirectory() as tmp:
-        subprocess.check_call([exe, str(dim), str(degree), str(ref), mesh, op, str(dirichlet), tmp])
+        subprocess.check_call([exe, str(dim), str(degree), str(ref), mesh, op, str(dirichlet), tmp] + extra)
         man = json.load(open(os.path.join(tmp, "manifest.json")))
         out = {}
         for k, v in man.items():

@@ -48,3 +48,16 @@ def test_invalid_arguments_fail_loudly():
         dealii_b200.HyperCubeMesh(4, 2, refinements=1)
     with pytest.raises(dealii_b200.B200MFError):
         dealii_b200.HyperCubeMesh(3, 9, refinements=1)
+
+
+@pytest.mark.parametrize("name,degree,refinements,dirichlet", [("lex_q4", 4, 2, True), ("lex_q2", 2, 3, False)])
+def test_lexicographic_numbering_equals_dof_renumbering_lexicographic(name, degree, refinements, dirichlet):
+    """numbering="lexicographic" reproduces DoFRenumbering::lexicographic of the reference itself
+    (tests/golden/ref/lex_*.npz were dumped by deal.II after that call)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref", name + ".npz"))
+    m = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements, numbering="lexicographic",
+                                  dirichlet_boundary=dirichlet)
+    assert np.array_equal(m.l2g, z["local_to_global"].reshape(-1, (degree + 1) ** 3))
+    if dirichlet:
+        assert np.array_equal(np.sort(m.boundary_dofs), z["constrained_dofs"])

@@ -3,15 +3,15 @@ import json, sys, time
 import torch
 import dealii_b200
 
-def run(degree, refinements, number, reps=20):
-    mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements)
+def run(degree, refinements, number, numbering="default", reps=20):
+    mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements, numbering=numbering)
     t0 = time.time()
     mf = dealii_b200.MatrixFree(number).reinit_from_mesh(mesh)
     setup_s = time.time() - t0
     op = dealii_b200.LaplaceOperator(mf)
     x = torch.rand(mf.n_owned, dtype=mf.torch_dtype, device="cuda")
     y = mf.initialize_dof_vector()
-    out = dict(degree=degree, n_dofs=mf.n_owned, number=number, setup_s=round(setup_s, 2), bulk=mf.bulk_info())
+    out = dict(degree=degree, n_dofs=mf.n_owned, number=number, numbering=numbering, setup_s=round(setup_s, 2), info=mf.bulk_info())
     ref = None
     for mode, path in (("bulk", 2), ("coloured", 1), ("map", 0)):
         if mf.select_brick_path(path) != path:
@@ -37,6 +37,6 @@ if __name__ == "__main__":
     cases = [(4, 5, "f64"), (4, 7, "f64"), (4, 7, "f32"), (3, 7, "f64"), (5, 6, "f64"), (2, 7, "f64"),
              (1, 8, "f64"), (6, 6, "f64"), (8, 5, "f64")]
     if len(sys.argv) > 1:
-        cases = [(int(sys.argv[1]), int(sys.argv[2]), sys.argv[3])]
+        cases = [(int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]) + tuple(sys.argv[4:5])]
     for c in cases:
         run(*c)
