@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -91,7 +92,8 @@ int main() {
 
   const size_t n = pv.n_owned, nt = pv.n_owned + pv.n_ghost;
   double *x, *b, *y, *diag, *scal;
-  cudaMalloc(&x, nt * 8); cudaMalloc(&b, nt * 8); cudaMalloc(&y, nt * 8); cudaMalloc(&diag, nt * 8); cudaMalloc(&scal, 64);
+  for (double **v : {&x, &b, &y, &diag}) cudaMalloc(reinterpret_cast<void **>(v), nt * 8);
+  cudaMalloc(reinterpret_cast<void **>(&scal), 64);
   cudaMemset(x, 0, nt * 8); cudaMemset(b, 0, nt * 8); cudaMemset(y, 0, nt * 8);
   const b200mf_operator op = {nullptr, nullptr, 1.0, 0.0};
 

@@ -27,7 +27,7 @@ def run(exe, world, tmp):
                WORLD_SIZE=str(world), B200MF_ID_FILE=os.path.join(tmp, f"id{world}"), B200MF_REFINEMENTS="3")
     # NCCL comes from the torch wheel in this image (a deal.II host would link the system libnccl)
     import nvidia.nccl
-    env["LD_LIBRARY_PATH"] = os.path.join(os.path.dirname(nvidia.nccl.__path__[0] + "/"), "lib") + ":" + env["LD_LIBRARY_PATH"]
+    env["LD_LIBRARY_PATH"] = os.path.join(list(nvidia.nccl.__path__)[0], "lib") + ":" + env["LD_LIBRARY_PATH"]
     procs = [subprocess.Popen([exe], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.PIPE, text=True) for r in range(world)]
     outs = [p.communicate(timeout=300) for p in procs]
