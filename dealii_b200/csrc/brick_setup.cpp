@@ -45,8 +45,10 @@ static int build_colouring(const b200mf_setup_desc &d, Setup &s, std::vector<uin
   const int L = b * p + 1;
   const uint64_t L3 = (uint64_t)L * L * L, W = (uint64_t)b * b * b, npc = (uint64_t)n * n * n;
   const uint64_t n_total = s.n_owned + s.n_ghost;
-  const uint64_t ni = (s.n_cells_interior > 0 && s.n_cells_interior < s.n_cells) ? s.n_cells_interior : s.n_cells;
-  const bool pieces = s.n_ghost > 0 && ni < s.n_cells;
+  // same convention as dist_vmult_impl (comm.cu): with ghost dofs, cells [0, n_cells_interior) are the
+  // interior (possibly none); without, everything is
+  const uint64_t ni = s.n_ghost > 0 ? std::min(s.n_cells_interior, s.n_cells) : s.n_cells;
+  const bool pieces = s.n_ghost > 0;
   K.half = pieces ? (ni / 2) / W * W : ni;
   auto piece_of_cell = [&](uint64_t c) -> int { return !pieces ? 0 : (c >= ni ? 1 : (c < K.half ? 0 : 2)); };
   // dofs the per-cell kernels accumulate into (atomics on zeroed entries): never stored by a brick

@@ -395,7 +395,9 @@ static int dist_vmult_impl(const Setup &s, const b200mf_partitioner &p, const b2
   b200mf_comm *c = p.comm;
   B200MF_REQUIRE(c, "partitioner has no communicator");
   cudaStream_t cs = c->comm_stream;
-  const uint64_t ni = s.n_cells_interior ? s.n_cells_interior : s.n_cells, nc = s.n_cells;
+  // cells [0, ni) touch no ghost dof.  A setup WITH ghost dofs whose caller reports 0 interior cells (every
+  // block of cells touches the interface, or no split was given) runs all cells after the ghost update.
+  const uint64_t nc = s.n_cells, ni = s.n_ghost > 0 ? std::min(s.n_cells_interior, nc) : nc;
   const uint64_t W = s.n_bricks ? (uint64_t)s.brick_b * s.brick_b * s.brick_b : 1;
   const bool coloured = coloured_enabled(s, op);
   const uint64_t half = coloured ? s.colouring.half : (ni / 2) / W * W; // pieces never cut a brick

@@ -110,7 +110,8 @@ typedef struct {
 
   /* Cells [0, n_cells_interior) touch no ghost dof and may run while the ghost exchange
    * is in flight (the colour-0/2 vs colour-1 split of
-   * portable_matrix_free.templates.h:1090-1133).  0 => no split.                        */
+   * portable_matrix_free.templates.h:1090-1133).  Without ghost dofs the value is ignored; with ghost
+   * dofs 0 means "no cell may run before the ghost values have arrived".                          */
   uint64_t n_cells_interior;
 } b200mf_setup_desc;
 
