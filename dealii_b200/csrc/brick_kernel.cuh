@@ -370,4 +370,213 @@ brick_cartesian_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strided bricks in z slabs: the same brick operator for numberings in which the lattice of a brick
+// is an affine image of the dof indices (STRIDED above), with the brick processed in NS slabs of
+// b / NS cell layers.  The x and y sweeps act inside one z plane, so only the planes of the current
+// slab have to be resident: two arrays of L x L x (b p / NS + 1) values instead of L^3 -- 41.6 KB
+// instead of 78.6 KB for Q4 FP64, i.e. four resident CTAs per SM instead of two for a kernel that is
+// latency bound once the index traffic is gone (profiles/r02_brick_strided_q4_f64_ncu.txt:
+// warps_active 30 %).  The z sweep carries its partial sums and the last plane's inputs across the
+// slabs in registers, exactly as it carries them across the cell blocks inside a slab.
+template <int p, int b, int NS, typename Number>
+struct SlabCfg {
+  static constexpr int n = p + 1;
+  static constexpr int L = b * p + 1, L2 = L * L;
+  static constexpr int CS = b / NS;           // cell layers per slab
+  static constexpr int NZ = CS * p + 1;       // planes of the first slab (the others hold CS p)
+  static constexpr int threads = ((L2 + 31) / 32) * 32;
+  static constexpr size_t smem_bytes = 2 * sizeof(Number) * L2 * NZ;
+};
+
+template <int p, int b, int NS, typename Number, bool DOT>
+__global__ void __launch_bounds__(SlabCfg<p, b, NS, Number>::threads, DOT ? 2 : 3)
+brick_strided_slab_kernel(const __grid_constant__ BrickKernelParams<p, Number> prm) {
+  using Cfg = SlabCfg<p, b, NS, Number>;
+  constexpr int n = p + 1, L = Cfg::L, L2 = Cfg::L2, CS = Cfg::CS;
+  constexpr uint32_t CBIT = B200MF_L2G_CONSTRAINED;
+  extern __shared__ __align__(16) unsigned char brick_smem[];
+  Number *P0 = reinterpret_cast<Number *>(brick_smem);
+  Number *P1 = P0 + L2 * Cfg::NZ;
+  const int tid = threadIdx.x;
+  const unsigned long long brick = prm.list ? (unsigned long long)__ldg(prm.list + prm.brick_begin + blockIdx.x)
+                                            : prm.brick_begin + blockIdx.x;
+  const Number *__restrict__ src = prm.src;
+  Number *__restrict__ dst = prm.dst;
+  const uint4 sd = __ldg(prm.strided + brick);
+  const bool col = tid < L2;                 // thread <-> lattice column (x, y)
+  const int la = tid % L, lb = tid / L;
+  const uint32_t line = sd.x + la + sd.y * lb;
+  const uint32_t cbits = sd.w >> 6;
+  const bool cons_xy = cbits != 0u && on_flagged_face<L>(cbits & 15u, la, lb, 1);
+  const bool shared_xy = on_flagged_face<L>(sd.w & 15u, la, lb, 1);
+  auto word = [&](int z) -> uint32_t {
+    const bool shared = shared_xy || ((sd.w & 16u) && z == 0) || ((sd.w & 32u) && z == L - 1);
+    const bool cons = cons_xy || ((cbits & 16u) && z == 0) || ((cbits & 32u) && z == L - 1);
+    return (line + sd.z * z) | (shared ? 0u : B200MF_MAP_COMPLETE) | (cons ? CBIT : 0u);
+  };
+  double dot = 0.0;
+  auto emit = [&](uint32_t m, Number v, Number u, Number o) {
+    if (!(m & CBIT)) {
+      Number *d = dst + (m & B200MF_MAP_INDEX);
+      if (m & B200MF_MAP_COMPLETE) *d = v + o;
+      else atomicAdd(d, v);
+      if (DOT) dot += double(u) * double(v);
+    }
+  };
+  // carried across the slabs by the z sweep of this thread's column
+  Number inC[n], inD[n], cV = Number(0);
+
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int zb = sl * CS * p + (sl > 0 ? 1 : 0); // first plane this slab loads
+    const int nz = CS * p + (sl == 0 ? 1 : 0);     // number of planes it loads
+    if (sl > 0) __syncthreads();                   // the previous slab's z sweep has read P0 / P1
+    // ---- read_dof_values of the slab: thread (x, y) walks its column, lanes on consecutive dofs
+    if (col) {
+      Number val[Cfg::NZ];
+#pragma unroll
+      for (int zl = 0; zl < Cfg::NZ; ++zl)
+        if (zl < nz) {
+          const int z = zb + zl;
+          const bool cons = cons_xy || ((cbits & 16u) && z == 0) || ((cbits & 32u) && z == L - 1);
+          val[zl] = cons ? Number(0) : __ldg(src + line + sd.z * z);
+        }
+#pragma unroll
+      for (int zl = 0; zl < Cfg::NZ; ++zl)
+        if (zl < nz) P0[tid + zl * L2] = val[zl];
+    }
+    __syncthreads();
+    const bool rowt = tid < L * nz;                // thread <-> lattice row inside the slab
+    // ---- x sweep: A = Mx u -> P0 (in place), B = Kx u -> P1; thread <-> (y, zl)
+    if (rowt) {
+      Number *l0 = P0 + L * tid, *l1 = P1 + L * tid;
+      Number in[n], cA = Number(0), cB = Number(0);
+      in[0] = l0[0];
+#pragma unroll
+      for (int c = 0; c < b; ++c) {
+#pragma unroll
+        for (int k = 1; k < n; ++k) in[k] = l0[c * p + k];
+        EoHalf<Number, n> x;
+        eo_split<Number, n>(in, x);
+        EoAcc<Number, n> a;
+        Number oA[n], oB[n];
+        eo_mac<true, Number, n>(prm.mat.M, x, a);
+        eo_join<Number, n>(a, oA);
+        eo_mac<true, Number, n>(prm.mat.Kx, x, a);
+        eo_join<Number, n>(a, oB);
+        if (c > 0) { oA[0] += cA; oB[0] += cB; }
+#pragma unroll
+        for (int k = 0; k < p; ++k) {
+          l0[c * p + k] = oA[k];
+          l1[c * p + k] = oB[k];
+        }
+        cA = oA[p];
+        cB = oB[p];
+        in[0] = in[p];
+      }
+      l0[L - 1] = cA;
+      l1[L - 1] = cB;
+    }
+    __syncthreads();
+    // ---- y sweep: C = My A -> P0, D = Ky A + My B -> P1 (in place); thread <-> (x, zl)
+    if (rowt) {
+      Number *l0 = P0 + la + L2 * lb, *l1 = P1 + la + L2 * lb;
+      Number inA[n], inB[n], cC = Number(0), cD = Number(0);
+      inA[0] = l0[0];
+      inB[0] = l1[0];
+#pragma unroll
+      for (int c = 0; c < b; ++c) {
+#pragma unroll
+        for (int k = 1; k < n; ++k) {
+          inA[k] = l0[(c * p + k) * L];
+          inB[k] = l1[(c * p + k) * L];
+        }
+        EoHalf<Number, n> xa, xb;
+        eo_split<Number, n>(inA, xa);
+        eo_split<Number, n>(inB, xb);
+        EoAcc<Number, n> a;
+        Number oC[n], oD[n];
+        eo_mac<true, Number, n>(prm.mat.M, xa, a);
+        eo_join<Number, n>(a, oC);
+        eo_mac<true, Number, n>(prm.mat.Ky, xa, a);
+        eo_mac<false, Number, n>(prm.mat.M, xb, a);
+        eo_join<Number, n>(a, oD);
+        if (c > 0) { oC[0] += cC; oD[0] += cD; }
+#pragma unroll
+        for (int k = 0; k < p; ++k) {
+          l0[(c * p + k) * L] = oC[k];
+          l1[(c * p + k) * L] = oD[k];
+        }
+        cC = oC[p];
+        cD = oD[p];
+        inA[0] = inA[p];
+        inB[0] = inB[p];
+      }
+      l0[(L - 1) * L] = cC;
+      l1[(L - 1) * L] = cD;
+    }
+    __syncthreads();
+    // ---- z sweep over the cell layers of this slab: v = Kz' C + Mz D, written straight to dst
+    if (col) {
+      const Number *l0 = P0 + tid, *l1 = P1 + tid;
+      if (sl == 0) {
+        inC[0] = l0[0];
+        inD[0] = l1[0];
+      }
+#pragma unroll
+      for (int cc = 0; cc < CS; ++cc) {
+        const int c = sl * CS + cc; // cell layer of the brick
+        Number ui[p], old[p];
+        if (DOT) {
+#pragma unroll
+          for (int k = 0; k < p; ++k)
+            ui[k] = (word(c * p + k) & CBIT) ? Number(0) : __ldg(src + (word(c * p + k) & B200MF_MAP_INDEX));
+        }
+        if (!prm.overwrite) {
+#pragma unroll
+          for (int k = 0; k < p; ++k)
+            old[k] = (word(c * p + k) & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE
+                         ? dst[word(c * p + k) & B200MF_MAP_INDEX]
+                         : Number(0);
+        }
+#pragma unroll
+        for (int k = 1; k < n; ++k) {
+          inC[k] = l0[(c * p + k - zb) * L2];
+          inD[k] = l1[(c * p + k - zb) * L2];
+        }
+        EoHalf<Number, n> xc, xd;
+        eo_split<Number, n>(inC, xc);
+        eo_split<Number, n>(inD, xd);
+        EoAcc<Number, n> a;
+        Number oV[n];
+        eo_mac<true, Number, n>(prm.mat.Kz, xc, a);
+        eo_mac<false, Number, n>(prm.mat.M, xd, a);
+        eo_join<Number, n>(a, oV);
+        if (c > 0) oV[0] += cV;
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+          emit(word(c * p + k), oV[k], DOT ? ui[k] : Number(0), prm.overwrite ? Number(0) : old[k]);
+        cV = oV[p];
+        inC[0] = inC[p];
+        inD[0] = inD[p];
+      }
+      if (sl == NS - 1) {
+        const uint32_t m = word(L - 1);
+        Number u = Number(0);
+        if (DOT && !(m & CBIT)) u = __ldg(src + (m & B200MF_MAP_INDEX));
+        Number o = Number(0);
+        if (!prm.overwrite && (m & (CBIT | B200MF_MAP_COMPLETE)) == B200MF_MAP_COMPLETE) o = dst[m & B200MF_MAP_INDEX];
+        emit(m, cV, u, o);
+      }
+    }
+  }
+  if (DOT && prm.dot_accum != nullptr) {
+    dot = block_sum(dot);
+    if (tid == 0) atomicAdd(prm.dot_accum, dot);
+  }
+}
+
 } // namespace b200mf

@@ -197,6 +197,20 @@ int launch_bricks_one(const Setup &s, const b200mf_operator &op, void *dst, cons
   prm.list = list;
   prm.overwrite = list ? 2 : (overwrite ? 1 : 0);
   prm.strided = STRIDED ? s.d_brick_strided : nullptr;
+  if constexpr (STRIDED && b >= 2) {
+    // z slabs (two per brick) when the two full lattice arrays allow only two CTAs per SM: more
+    // resident warps for a kernel that is latency bound once the index traffic is gone
+    static const bool slabs_off = std::getenv("B200MF_NO_SLABS") != nullptr;
+    if (Cfg::smem_bytes > 64 * 1024 && !slabs_off) {
+      using SCfg = SlabCfg<p, b, 2, Number>;
+      auto skernel = brick_strided_slab_kernel<p, b, 2, Number, DOT>;
+      B200MF_CUDA_CHECK(cudaFuncSetAttribute(skernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg::smem_bytes));
+      skernel<<<(unsigned)n_bricks, SCfg::threads, SCfg::smem_bytes, stream>>>(prm);
+      count_launch();
+      B200MF_CUDA_CHECK(cudaGetLastError());
+      return B200MF_OK;
+    }
+  }
   auto kernel = brick_cartesian_kernel<p, b, Number, DOT, STRIDED>;
   // (the attribute is per device: set it on every launch, it is a cheap driver call)
   B200MF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
