@@ -5,3 +5,4 @@ from .matrix_free import (DiagonalMatrix, HelmholtzOperator, HyperCubeMesh, Lapl
                           MatrixFree, MatrixFreeOperator, PreconditionChebyshev, SolverCG,
                           SolverControl)
 from ._lib import B200MFError  # noqa: F401
+from .multigrid import GeometricMultigrid  # noqa: F401

@@ -69,6 +69,18 @@ class SolverResult(C.Structure):
                 ("operator_applications", u64)]
 
 
+class MgDesc(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("levels", C.POINTER(vp)), ("operators", C.POINTER(Operator)),
+                ("child_cells", C.POINTER(vp)), ("smoother_degree", C.c_int32),
+                ("smoothing_range", C.c_double), ("eig_cg_n_iterations", C.c_int32),
+                ("coarse_tolerance", C.c_double), ("safety_factor", C.c_double)]
+
+
+class MgLevelInfo(C.Structure):
+    _fields_ = [("eig_min", C.c_double), ("eig_max", C.c_double), ("degree", C.c_int32),
+                ("eig_cg_iterations", C.c_int32), ("n_dofs", u64), ("inverse_diagonal", vp)]
+
+
 class PartitionerInfo(C.Structure):
     _fields_ = [("n_owned", u64), ("n_ghost", u64), ("n_import", u64),
                 ("n_ghost_targets", C.c_int), ("n_import_targets", C.c_int),
@@ -157,6 +169,14 @@ SYMBOLS = {
                                        C.POINTER(SolverResult), vp]),
     "b200mf_cg_solve": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
                                   C.POINTER(SolverResult), vp]),
+    "b200mf_mg_create": (C.c_int, [C.POINTER(MgDesc), C.POINTER(vp), vp]),
+    "b200mf_mg_destroy": (None, [vp]),
+    "b200mf_mg_get_level_info": (C.c_int, [vp, C.c_int, C.POINTER(MgLevelInfo)]),
+    "b200mf_mg_prolongate": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    "b200mf_mg_restrict_and_add": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    "b200mf_mg_vcycle": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    "b200mf_mg_cg_solve": (C.c_int, [vp, vp, C.POINTER(Operator), C.c_double, C.c_int, vp, vp,
+                                     C.POINTER(SolverResult), vp]),
     "b200mf_cg_solve_host": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
                                        C.POINTER(SolverResult)]),
     "b200mf_mesh_create": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(vp)]),

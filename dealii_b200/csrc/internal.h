@@ -249,6 +249,8 @@ void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
                            std::vector<double> &q_points, std::vector<double> &subface);
 
+void build_prolongation_1d(int degree, std::vector<double> &P);
+
 template <typename Number, int n>
 void fill_shape_data(const Setup &s, ShapeData<Number, n> &out);
 

@@ -107,6 +107,25 @@ void build_fe_q_support_points(int degree, std::vector<double> &points) {
   points.assign(xn.begin(), xn.end());
 }
 
+// 1D prolongation of FE_Q(degree) from a cell to its two children: P[X * n + i] = l_i(x_X), X = 0..2p the
+// nodes of both children in the parent's unit cell (child 0: X <= p at gl[X] / 2, child 1 at
+// 1/2 + gl[X - p] / 2); the tensor product of three of them is the embedding matrix deal.II's
+// MGTransferMatrixFree applies cell by cell (multigrid/mg_transfer_internal.cc: setup_element_info,
+// "prolongation_matrix_1d")
+void build_prolongation_1d(int degree, std::vector<double> &P) {
+  const int n = degree + 1, M = 2 * degree + 1;
+  const std::vector<long double> xn = gauss_lobatto_points(n);
+  P.assign((size_t)M * n, 0.0);
+  for (int X = 0; X < M; ++X) {
+    const long double x = X <= degree ? 0.5L * xn[X] : 0.5L + 0.5L * xn[X - degree];
+    for (int i = 0; i < n; ++i) {
+      long double v, d;
+      lagrange(xn, x, i, v, d);
+      P[(size_t)X * n + i] = (double)v;
+    }
+  }
+}
+
 void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
                            std::vector<double> &q_points, std::vector<double> &subface) {

@@ -341,6 +341,13 @@ class SolverCG:
 
     def solve(self, A, x, b, preconditioner=None):
         mf = A.mf
+        if hasattr(preconditioner, "solve") and hasattr(preconditioner, "level_operators"):
+            # PreconditionMG: the V-cycle of dealii_b200.multigrid.GeometricMultigrid
+            code, res = preconditioner.solve(A, x, b, self.control.tolerance, self.control.max_steps)
+            self.result = res
+            self.control._last_step, self.control._last_value = res.iterations, res.residual
+            L.check(code)
+            return res
         sd = L.SolverDesc()
         sd.tolerance, sd.max_iterations = self.control.tolerance, self.control.max_steps
         keep = None

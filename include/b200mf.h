@@ -431,6 +431,61 @@ int b200mf_cg_solve_host(const b200mf_setup *s, const b200mf_operator *op,
                          b200mf_solver_result *result);
 
 /* ------------------------------------------------------------------------------------
+ * Geometric multigrid: the V-cycle preconditioner of step-37 with the
+ * engine's operator on every level.  Replaces, on the device,
+ *   Multigrid::level_v_step                       multigrid/multigrid.templates.h:112-171
+ *   PreconditionMG::vmult                         multigrid/multigrid.h
+ *   MGTransferMatrixFree::prolongate / restrict_and_add   multigrid/mg_transfer_matrix_free.h
+ *   mg::SmootherRelaxation<PreconditionChebyshev> (degree 5, range 15, 10 Lanczos iterations) and
+ *   MGCoarseGridApplySmoother (Chebyshev in solver mode on level 0)   examples/step-37/step-37.cc:956-988
+ * Levels are serial, globally refined meshes of one number type (float levels under a double
+ * CG as in step-37 are supported: b200mf_mg_vcycle / b200mf_mg_cg_solve convert at the top).
+ * ---------------------------------------------------------------------------------- */
+typedef struct b200mf_mg b200mf_mg;
+
+typedef struct {
+  int32_t n_levels;                    /* coarsest level first                                         */
+  const b200mf_setup *const *levels;   /* n_levels setups; level l+1 is level l refined once           */
+  const b200mf_operator *operators;    /* n_levels operators (coefficient arrays belong to their level) */
+  /* NULL: the children of cell c of level l are the cells (c << dim) + k of level l+1, k = x + 2 y + 4 z
+   * (b200mf_mesh_create in Morton order, deal.II's refine_global); else n_levels - 1 HOST arrays
+   * [n_cells(l)][2^dim] with the cell indices of the children on level l+1                            */
+  const uint32_t *const *child_cells;
+  int32_t smoother_degree;             /* PreconditionChebyshev::AdditionalData::degree (step-37: 5)    */
+  double smoothing_range;              /* ... smoothing_range (15)                                     */
+  int32_t eig_cg_n_iterations;         /* ... eig_cg_n_iterations (10)                                 */
+  double coarse_tolerance;             /* level 0: smoothing_range < 1 = relative tolerance of the
+                                          Chebyshev solver, its degree from the error estimate (1e-3)  */
+  double safety_factor;                /* on the largest Lanczos eigenvalue; 0 => 1.2                  */
+} b200mf_mg_desc;
+
+typedef struct {
+  double eig_min, eig_max;             /* estimates of the Jacobi-preconditioned level operator        */
+  int32_t degree;                      /* polynomial degree used on this level                         */
+  int32_t eig_cg_iterations;
+  uint64_t n_dofs;
+  const void *inverse_diagonal;        /* DEVICE, level number type                                    */
+} b200mf_mg_level_info;
+
+/* Computes the level diagonals, transfer weights and eigenvalue estimates (the lazy
+ * estimate_eigenvalues of the reference's smoothers happens here).  The setups must outlive it. */
+int b200mf_mg_create(const b200mf_mg_desc *desc, b200mf_mg **out, void *stream);
+void b200mf_mg_destroy(b200mf_mg *mg);
+int b200mf_mg_get_level_info(const b200mf_mg *mg, int level, b200mf_mg_level_info *info);
+/* MGTransferMatrixFree::prolongate(to_level, dst, src): dst (level to_level) = P src (level to_level-1);
+ * restrict_and_add(from_level, dst, src): dst (level from_level-1) += P^T src.  Level number type. */
+int b200mf_mg_prolongate(const b200mf_mg *mg, int to_level, void *dst, const void *src, void *stream);
+int b200mf_mg_restrict_and_add(const b200mf_mg *mg, int from_level, void *dst, const void *src,
+                               void *stream);
+/* PreconditionMG::vmult: dst = one V-cycle applied to src, vectors of type `number` on the finest level. */
+int b200mf_mg_vcycle(b200mf_mg *mg, int number, void *dst, const void *src, void *stream);
+/* SolverCG on `system` (the finest-level operator, possibly of another number type than the levels)
+ * preconditioned by the V-cycle; tolerance is absolute (SolverControl).                               */
+int b200mf_mg_cg_solve(b200mf_mg *mg, const b200mf_setup *system, const b200mf_operator *op,
+                       double tolerance, int max_iterations, void *x, const void *b,
+                       b200mf_solver_result *result, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Synthetic mesh + DoF generator (HOST).  Stands in for GridGenerator::hyper_cube +
  * Triangulation::refine_global / subdivided_hyper_cube + DoFHandler::distribute_dofs
  * (source/dofs/dof_handler_policy.cc:1676-1719) for the >=100 M-DoF runs the reference's

@@ -22,6 +22,12 @@ for deg in ${DEGREES:-1 2 3 4 5 6 7 8}; do
     pids+=($!)
   fi
 done
+for deg in ${GMG_DEGREES:-1 2 3 4}; do
+  if [ ! -x "$BIN/ref_gmg_q$deg" ] || [ "$HERE/ref_gmg.cc" -nt "$BIN/ref_gmg_q$deg" ]; then
+    ( $CXX $FLAGS -DREF_DEGREE=$deg $INC "$HERE/ref_gmg.cc" -o "$BIN/ref_gmg_q$deg" $LINK ) &
+    pids+=($!)
+  fi
+done
 if [ ! -x "$BIN/ref_bench" ] || [ "$HERE/ref_bench.cc" -nt "$BIN/ref_bench" ]; then
   ( $CXX $FLAGS $INC "$HERE/ref_bench.cc" -o "$BIN/ref_bench" $LINK ) &
   pids+=($!)

@@ -20,6 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 OUT = os.path.join(ROOT, "tests", "golden", "ref")
+OUT_GMG = os.path.join(ROOT, "tests", "golden", "ref_gmg")
 
 # name: (dim, degree, refinements, mesh, op, dirichlet, keep_jacobians)
 CASES = {
@@ -53,6 +54,42 @@ CASES = {
     "d2_q4_cartesian": (2, 4, 3, "cartesian", "laplace", 1, False),
 }
 
+# geometric multigrid of step-37 (oracle/ref_drivers/ref_gmg.cc): name: (dim, degree, refinements, level number,
+# coefficient).  Big vectors are dropped for the larger cases (iteration counts / eigenvalues / norms stay).
+GMG_CASES = {
+    "gmg_q2_r2_f64": (3, 2, 2, "f64", "constant", True),
+    "gmg_q2_r3_f64_step37": (3, 2, 3, "f64", "step37", True),
+    "gmg_q4_r2_f64": (3, 4, 2, "f64", "constant", True),
+    "gmg_q4_r2_f32_step37": (3, 4, 2, "f32", "step37", True),
+    "gmg_q1_r3_f64": (3, 1, 3, "f64", "constant", True),
+    "gmg_q3_r3_f32": (3, 3, 3, "f32", "constant", False),
+    "gmg_q2_r5_f32_step37": (3, 2, 5, "f32", "step37", False),
+    "gmg_q4_r4_f64": (3, 4, 4, "f64", "constant", False),
+    "gmg_d2_q3_r4_f64": (2, 3, 4, "f64", "step37", True),
+}
+
+
+def run_gmg_case(name, spec):
+    dim, degree, ref, number, coef, keep_vectors = spec
+    exe = os.path.join(BIN, f"ref_gmg_q{degree}")
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.check_call([exe, str(dim), str(ref), number, coef, tmp])
+        man = json.load(open(os.path.join(tmp, "manifest.json")))
+        out = {}
+        for k, v in man.items():
+            if isinstance(v, dict):
+                if not keep_vectors and not k.startswith("level_l2g_0"):
+                    continue
+                if k == "level_l2g_%d" % ref and not keep_vectors:
+                    continue
+                out[k] = np.fromfile(os.path.join(tmp, v["file"]), dtype=v["dtype"])
+                assert out[k].size == v["size"]
+            else:
+                out[k] = np.array(v)
+        os.makedirs(OUT_GMG, exist_ok=True)
+        np.savez_compressed(os.path.join(OUT_GMG, name + ".npz"), **out)
+        print(name, {k: v.item() for k, v in out.items() if v.ndim == 0})
+
 
 def run_case(name, spec):
     dim, degree, ref, mesh, op, dirichlet, keep_jac = spec[:7]
@@ -78,6 +115,9 @@ def run_case(name, spec):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(GMG_CASES))
     for n in names:
-        run_case(n, CASES[n])
+        if n in GMG_CASES:
+            run_gmg_case(n, GMG_CASES[n])
+        else:
+            run_case(n, CASES[n])
