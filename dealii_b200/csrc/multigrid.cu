@@ -344,7 +344,7 @@ static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
     uint64_t extra = 0;
     if ((rc = estimate_eigenvalues<Number>(s, L.op, (const Number *)L.inv_diag, eig_its, 0,
                                            d.safety_factor > 0 ? d.safety_factor : 1.2, st, L.lmin, L.lmax, extra,
-                                           &L.eig_cg_iterations)) != B200MF_OK)
+                                           &L.eig_cg_iterations, /*zero_constrained=*/false)) != B200MF_OK)
       return rc;
     mg.vmults += extra;
     B200MF_REQUIRE(std::isfinite(L.lmin) && std::isfinite(L.lmax) && L.lmin > 0.0 && L.lmax >= L.lmin,

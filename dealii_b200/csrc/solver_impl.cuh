@@ -387,7 +387,8 @@ struct Chebyshev {
 template <typename Number>
 static int estimate_eigenvalues(Setup &s, const b200mf_operator &op, const Number *d, int eig_cg_n_iterations,
                                 uint64_t first_owned_global_index, double safety_factor, cudaStream_t st,
-                                double &lmin, double &lmax, uint64_t &vmults, int *cg_iterations) {
+                                double &lmin, double &lmax, uint64_t &vmults, int *cg_iterations,
+                                bool zero_constrained = true) {
   lmin = lmax = 1.0;
   if (cg_iterations) *cg_iterations = 0;
   if (eig_cg_n_iterations <= 0) return B200MF_OK;
@@ -405,8 +406,9 @@ static int estimate_eigenvalues(Setup &s, const b200mf_operator &op, const Numbe
   const double mean = s.h_pinned[0] / double(n);
   shift_kernel<Number><<<grid, kVecThreads, 0, st>>>(t1, Number(-mean), n);
   count_launch();
-  // constraints.set_zero(temp_vector1)
-  if ((rc = set_constrained_impl(s, t1, 0.0, st)) != B200MF_OK) return rc;
+  // constraints.set_zero(temp_vector1): AdditionalData::constraints -- empty in step-37's smoothers, where
+  // the operator itself is the identity on constrained rows
+  if (zero_constrained && (rc = set_constrained_impl(s, t1, 0.0, st)) != B200MF_OK) return rc;
   // temp_vector1.all_zero(): every dof constrained (a one-cell level) -> both estimates stay 1
   B200MF_CUDA_CHECK(cudaMemsetAsync(s.d_scratch + 57, 0, sizeof(double), st));
   dot2_kernel<Number><<<grid, kVecThreads, 0, st>>>(t1, t1, n, s.d_scratch + 57);

@@ -4,7 +4,9 @@
 # (bench.py --impl reference), never part of the product path.
 #
 # Recipe = SURVEY.md section 8(c) / BASELINE.md section 3 (serial, Release, bundled boost + Kokkos-Serial,
-# no MPI / LAPACK / TBB / p4est: none of them is in this image).  -march=x86-64-v4 instead of
+# no MPI / TBB / p4est: none of them is in this image).  LAPACK (needed by SolverCG's eigenvalue estimate, i.e.
+# by PreconditionChebyshev and the multigrid of step-37) is the OpenBLAS inside this image's Python
+# environment (opencv's libopenblasp with plain dstev_ ... symbols) when it is there, else OFF.  -march=x86-64-v4 instead of
 # -march=native so the binaries run on the GPU box's host CPU too (AVX-512, VectorizedArray<double,8>).
 #
 # Outputs (all git-ignored):
@@ -26,10 +28,18 @@ if [ -f "$OUT/install/lib/libdeal_II.so" ] && [ -z "${FORCE:-}" ]; then
 fi
 mkdir -p "$OUT/build" "$OUT/install"
 cd "$OUT/build"
+BLASDIR="${BLASDIR:-/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs}"
+LAPACK_ARGS="-DDEAL_II_WITH_LAPACK=OFF"
+if ls "$BLASDIR"/libopenblasp-*.so >/dev/null 2>&1; then
+  OB="$(ls "$BLASDIR"/libopenblasp-*.so | head -1)"
+  GF="$(ls "$BLASDIR"/libgfortran-*.so* | head -1)"
+  QM="$(ls "$BLASDIR"/libquadmath-*.so* | head -1)"
+  LAPACK_ARGS="-DDEAL_II_WITH_LAPACK=ON -DLAPACK_LIBRARIES=$OB;$GF;$QM -DBLAS_LIBRARIES=$OB"
+fi
 cmake -G Ninja "$REF" \
   -DCMAKE_BUILD_TYPE=Release \
   -DCMAKE_CXX_FLAGS="-march=x86-64-v4 -mprefer-vector-width=512" \
-  -DDEAL_II_WITH_MPI=OFF -DDEAL_II_WITH_LAPACK=OFF -DDEAL_II_WITH_TBB=OFF -DDEAL_II_WITH_P4EST=OFF \
+  -DDEAL_II_WITH_MPI=OFF "$LAPACK_ARGS" -DDEAL_II_WITH_TBB=OFF -DDEAL_II_WITH_P4EST=OFF \
   -DDEAL_II_COMPONENT_EXAMPLES=OFF -DDEAL_II_ALLOW_AUTODETECTION=OFF \
   -DDEAL_II_FORCE_BUNDLED_BOOST=ON -DDEAL_II_FORCE_BUNDLED_KOKKOS=ON \
   -DCMAKE_INSTALL_PREFIX="$OUT/install" > "$OUT/configure.log" 2>&1

@@ -15,6 +15,13 @@ CXX=${CXX:-g++}
 FLAGS="-std=c++17 -O2 -fopenmp-simd -march=x86-64-v4 -mprefer-vector-width=512 -Wno-unused-parameter -Wno-deprecated-declarations"
 INC="-I$REF/include -I$REF/include/deal.II/bundled"
 LINK="-L$REF/lib -ldeal_II -Wl,-rpath,\$ORIGIN/../install/lib -rdynamic -ldl -lpthread"
+# the reference was configured with LAPACK = the OpenBLAS that ships inside this image's Python environment
+# (oracle/build_ref.sh); that library needs its libgfortran, which has no rpath of its own: link it into the
+# drivers so that it is loaded before OpenBLAS asks for it
+BLASDIR="${BLASDIR:-/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs}"
+if readelf -d "$REF/lib/libdeal_II.so" | grep -q openblas; then
+  LINK="$LINK -Wl,--no-as-needed $(ls $BLASDIR/libgfortran-*.so* | head -1) $(ls $BLASDIR/libquadmath-*.so* | head -1) -Wl,--as-needed -Wl,-rpath,$BLASDIR"
+fi
 pids=()
 for deg in ${DEGREES:-1 2 3 4 5 6 7 8}; do
   if [ ! -x "$BIN/ref_dump_q$deg" ] || [ "$HERE/ref_dump.cc" -nt "$BIN/ref_dump_q$deg" ]; then

@@ -102,7 +102,7 @@ struct Dump
     std::vector<double> out(v.size());
     for (unsigned int i = 0; i < v.size(); ++i)
       out[i] = v.local_element(i);
-    array(k, out, "f64");
+    array(k, out, "float64");
   }
 };
 
@@ -187,7 +187,7 @@ run(const unsigned int refinements, const bool variable, const std::string &outd
   mg_constrained_dofs.initialize(dof_handler);
   mg_constrained_dofs.make_zero_boundary_constraints(dof_handler, {0});
   MGLevelObject<LevelMatrix> mg_matrices(0, n_levels - 1);
-  const std::vector<unsigned int> h2l = FETools::hierarchic_to_lexicographic_numbering<dim>(degree);
+  const std::vector<unsigned int> l2h = FETools::lexicographic_to_hierarchic_numbering<dim>(degree);
   for (unsigned int level = 0; level < n_levels; ++level)
     {
       AffineConstraints<double> level_constraints(dof_handler.locally_owned_mg_dofs(level),
@@ -212,9 +212,9 @@ run(const unsigned int refinements, const bool variable, const std::string &outd
         {
           cell->get_mg_dof_indices(idx);
           for (unsigned int i = 0; i < idx.size(); ++i)
-            l2g.push_back(idx[h2l[i]]);
+            l2g.push_back(idx[l2h[i]]);
         }
-      dump.array("level_l2g_" + std::to_string(level), l2g, "u32");
+      dump.array("level_l2g_" + std::to_string(level), l2g, "uint32");
     }
 
   MGTransferMatrixFree<dim, LevelNumber> mg_transfer(mg_constrained_dofs);
