@@ -43,10 +43,10 @@ __global__ void mg_convert_kernel(To *dst, const From *src, uint64_t n) {
 constexpr int kMgThreads = 256;
 
 // index of lattice node (X, Y, Z) of coarse cell c in the fine level's vector
-template <int dim>
+template <int dim, int n>
 __device__ __forceinline__ uint32_t mg_fine_index(const uint32_t *l2g_f, const uint32_t *child, uint64_t c,
-                                                  int n, int npc, int X, int Y, int Z, int &shared_dirs) {
-  const int p = n - 1;
+                                                  int npc, int X, int Y, int Z, int &shared_dirs) {
+  constexpr int p = n - 1;
   const int cx = X > p, cy = Y > p, cz = (dim == 3) ? (Z > p) : 0;
   shared_dirs = (X == p) + (Y == p) + ((dim == 3) ? (Z == p) : 0);
   const int k = cx + 2 * cy + 4 * cz;
@@ -55,36 +55,38 @@ __device__ __forceinline__ uint32_t mg_fine_index(const uint32_t *l2g_f, const u
   return l2g_f[fine * npc + local];
 }
 
-template <typename Number, int dim>
+template <typename Number, int dim, int n>
 __global__ void __launch_bounds__(kMgThreads)
 mg_prolongate_kernel(Number *__restrict__ dst, const Number *__restrict__ src, const uint32_t *__restrict__ l2g_c,
                      const uint32_t *__restrict__ l2g_f, const uint32_t *__restrict__ child,
-                     const Number *__restrict__ P, int n, uint64_t n_coarse_cells) {
+                     const Number *__restrict__ P, uint64_t n_coarse_cells) {
   extern __shared__ __align__(16) unsigned char mg_smem[];
-  const int M = 2 * n - 1, nz = dim == 3 ? n : 1, Mz = dim == 3 ? M : 1;
-  const int npc = n * n * nz, cap = M * M * Mz;
+  constexpr int M = 2 * n - 1, nz = dim == 3 ? n : 1, Mz = dim == 3 ? M : 1;
+  constexpr int npc = n * n * nz, cap = M * M * Mz;
   Number *A = reinterpret_cast<Number *>(mg_smem), *B = A + cap, *Ps = B + cap;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < M * n; i += kMgThreads) Ps[i] = P[i];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < M * n; i += nthr) Ps[i] = P[i];
   for (uint64_t c = blockIdx.x; c < n_coarse_cells; c += gridDim.x) {
     __syncthreads();
-    for (int i = tid; i < npc; i += kMgThreads) {
+    for (int i = tid; i < npc; i += nthr) {
       const uint32_t idx = l2g_c[c * npc + i];
       A[i] = (idx & B200MF_L2G_CONSTRAINED) ? Number(0) : src[idx];
     }
     __syncthreads();
     // x: [z][y][i] -> [z][y][X]
-    for (int o = tid; o < n * nz * M; o += kMgThreads) {
+    for (int o = tid; o < n * nz * M; o += nthr) {
       const int X = o % M, zy = o / M;
       Number acc = 0;
+#pragma unroll
       for (int i = 0; i < n; ++i) acc += Ps[X * n + i] * A[zy * n + i];
       B[o] = acc;
     }
     __syncthreads();
     // y: [z][j][X] -> [z][Y][X]
-    for (int o = tid; o < nz * M * M; o += kMgThreads) {
+    for (int o = tid; o < nz * M * M; o += nthr) {
       const int X = o % M, Y = (o / M) % M, z = o / (M * M);
       Number acc = 0;
+#pragma unroll
       for (int j = 0; j < n; ++j) acc += Ps[Y * n + j] * B[(z * n + j) * M + X];
       A[o] = acc;
     }
@@ -92,44 +94,45 @@ mg_prolongate_kernel(Number *__restrict__ dst, const Number *__restrict__ src, c
     const Number *R = A;
     if (dim == 3) {
       // z: [k][Y][X] -> [Z][Y][X]
-      for (int o = tid; o < cap; o += kMgThreads) {
+      for (int o = tid; o < cap; o += nthr) {
         const int YX = o % (M * M), Z = o / (M * M);
         Number acc = 0;
-        for (int k = 0; k < n; ++k) acc += Ps[Z * n + k] * A[k * M * M + YX];
+  #pragma unroll
+      for (int k = 0; k < n; ++k) acc += Ps[Z * n + k] * A[k * M * M + YX];
         B[o] = acc;
       }
       __syncthreads();
       R = B;
     }
-    for (int o = tid; o < cap; o += kMgThreads) {
+    for (int o = tid; o < cap; o += nthr) {
       const int X = o % M, Y = (o / M) % M, Z = o / (M * M);
       int shared_dirs;
-      const uint32_t f = mg_fine_index<dim>(l2g_f, child, c, n, npc, X, Y, Z, shared_dirs);
+      const uint32_t f = mg_fine_index<dim, n>(l2g_f, child, c, npc, X, Y, Z, shared_dirs);
       // nodes on the faces of the coarse cell are written by every coarse cell that has them: same value
       if (!(f & B200MF_L2G_CONSTRAINED)) dst[f] = R[o];
     }
   }
 }
 
-template <typename Number, int dim>
+template <typename Number, int dim, int n>
 __global__ void __launch_bounds__(kMgThreads)
 mg_restrict_kernel(Number *__restrict__ dst, const Number *__restrict__ src, const Number *__restrict__ inv_valence,
                    const uint32_t *__restrict__ l2g_c, const uint32_t *__restrict__ l2g_f,
-                   const uint32_t *__restrict__ child, const Number *__restrict__ P, int n,
+                   const uint32_t *__restrict__ child, const Number *__restrict__ P,
                    uint64_t n_coarse_cells) {
   extern __shared__ __align__(16) unsigned char mg_smem[];
-  const int M = 2 * n - 1, nz = dim == 3 ? n : 1, Mz = dim == 3 ? M : 1;
-  const int npc = n * n * nz, cap = M * M * Mz;
+  constexpr int M = 2 * n - 1, nz = dim == 3 ? n : 1, Mz = dim == 3 ? M : 1;
+  constexpr int npc = n * n * nz, cap = M * M * Mz;
   Number *A = reinterpret_cast<Number *>(mg_smem), *B = A + cap, *Ps = B + cap;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < M * n; i += kMgThreads) Ps[i] = P[i];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < M * n; i += nthr) Ps[i] = P[i];
   for (uint64_t c = blockIdx.x; c < n_coarse_cells; c += gridDim.x) {
     __syncthreads();
     Number *G = dim == 3 ? B : A;
-    for (int o = tid; o < cap; o += kMgThreads) {
+    for (int o = tid; o < cap; o += nthr) {
       const int X = o % M, Y = (o / M) % M, Z = o / (M * M);
       int shared_dirs;
-      const uint32_t f = mg_fine_index<dim>(l2g_f, child, c, n, npc, X, Y, Z, shared_dirs);
+      const uint32_t f = mg_fine_index<dim, n>(l2g_f, child, c, npc, X, Y, Z, shared_dirs);
       // a node between children of this cell is seen 2^shared_dirs times inside it and 1/valence of its
       // value belongs to each fine cell
       G[o] = (f & B200MF_L2G_CONSTRAINED) ? Number(0) : src[f] * inv_valence[f] * Number(1 << shared_dirs);
@@ -137,26 +140,29 @@ mg_restrict_kernel(Number *__restrict__ dst, const Number *__restrict__ src, con
     __syncthreads();
     if (dim == 3) {
       // z^T: [Z][Y][X] -> [k][Y][X]
-      for (int o = tid; o < n * M * M; o += kMgThreads) {
+      for (int o = tid; o < n * M * M; o += nthr) {
         const int YX = o % (M * M), k = o / (M * M);
         Number acc = 0;
-        for (int Z = 0; Z < M; ++Z) acc += Ps[Z * n + k] * B[Z * M * M + YX];
+  #pragma unroll
+      for (int Z = 0; Z < M; ++Z) acc += Ps[Z * n + k] * B[Z * M * M + YX];
         A[o] = acc;
       }
       __syncthreads();
     }
     // y^T: [k][Y][X] -> [k][j][X]
-    for (int o = tid; o < nz * n * M; o += kMgThreads) {
+    for (int o = tid; o < nz * n * M; o += nthr) {
       const int X = o % M, j = (o / M) % n, k = o / (M * n);
       Number acc = 0;
+#pragma unroll
       for (int Y = 0; Y < M; ++Y) acc += Ps[Y * n + j] * A[(k * M + Y) * M + X];
       B[o] = acc;
     }
     __syncthreads();
     // x^T: [k][j][X] -> [k][j][i], added into the coarse vector
-    for (int o = tid; o < npc; o += kMgThreads) {
+    for (int o = tid; o < npc; o += nthr) {
       const int i = o % n, kj = o / n;
       Number acc = 0;
+#pragma unroll
       for (int X = 0; X < M; ++X) acc += Ps[X * n + i] * B[kj * M + X];
       const uint32_t idx = l2g_c[c * npc + o];
       if (!(idx & B200MF_L2G_CONSTRAINED)) atomicAdd(dst + idx, acc);
@@ -188,39 +194,67 @@ static size_t mg_smem_bytes(const Mg &mg) {
   return (2 * cap + (size_t)M * mg.n) * sizeof(Number);
 }
 
-template <typename Number>
-static int mg_prolongate(const Mg &mg, int to_level, Number *dst, const Number *src, cudaStream_t st) {
-  const MgLevel &f = mg.levels[to_level], &c = mg.levels[to_level - 1];
+// launch shape of the transfer kernels: small CTAs, many per SM (the sweeps of one coarse cell are short and
+// separated by barriers: concurrency across cells hides them)
+static int mg_threads() {
+  static const int v = getenv("B200MF_MG_THREADS") ? atoi(getenv("B200MF_MG_THREADS")) : 128;
+  return std::min(std::max(v, 32), kMgThreads);
+}
+static unsigned mg_grid(uint64_t n_cells) {
+  static const int per_sm = getenv("B200MF_MG_CTAS_PER_SM") ? atoi(getenv("B200MF_MG_CTAS_PER_SM")) : 16;
+  return (unsigned)std::min<uint64_t>(n_cells, 148ull * std::max(per_sm, 1));
+}
+
+template <typename Number, int dim, int n>
+static int mg_transfer_launch(const Mg &mg, int fine_level, bool prolongate, Number *dst, const Number *src,
+                              cudaStream_t st) {
+  const MgLevel &f = mg.levels[fine_level], &c = mg.levels[fine_level - 1];
   const size_t smem = mg_smem_bytes<Number>(mg);
-  const unsigned grid = (unsigned)std::min<uint64_t>(c.s->n_cells, 148ull * 8);
-  if (mg.dim == 3)
-    mg_prolongate_kernel<Number, 3><<<grid, kMgThreads, smem, st>>>(dst, src, c.s->d_l2g, f.s->d_l2g, f.d_child,
-                                                                    (const Number *)mg.d_P, mg.n, c.s->n_cells);
+  const unsigned grid = mg_grid(c.s->n_cells);
+  const int threads = mg_threads();
+  if (smem > 48 * 1024) {
+    // once per kernel and device would do; the call is cheap next to the launch
+    B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_prolongate_kernel<Number, dim, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_restrict_kernel<Number, dim, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (prolongate)
+    mg_prolongate_kernel<Number, dim, n><<<grid, threads, smem, st>>>(dst, src, c.s->d_l2g, f.s->d_l2g, f.d_child,
+                                                                      (const Number *)mg.d_P, c.s->n_cells);
   else
-    mg_prolongate_kernel<Number, 2><<<grid, kMgThreads, smem, st>>>(dst, src, c.s->d_l2g, f.s->d_l2g, f.d_child,
-                                                                    (const Number *)mg.d_P, mg.n, c.s->n_cells);
+    mg_restrict_kernel<Number, dim, n><<<grid, threads, smem, st>>>(dst, src, (const Number *)f.inv_valence, c.s->d_l2g,
+                                                                    f.s->d_l2g, f.d_child, (const Number *)mg.d_P,
+                                                                    c.s->n_cells);
   count_launch();
   B200MF_CUDA_CHECK(cudaGetLastError());
+  return B200MF_OK;
+}
+
+template <typename Number>
+static int mg_transfer(const Mg &mg, int fine_level, bool prolongate, Number *dst, const Number *src, cudaStream_t st) {
+#define B200MF_MG_CASE(N)                                                                                      \
+  case N:                                                                                                      \
+    return mg.dim == 3 ? mg_transfer_launch<Number, 3, N>(mg, fine_level, prolongate, dst, src, st)            \
+                       : mg_transfer_launch<Number, 2, N>(mg, fine_level, prolongate, dst, src, st);
+  switch (mg.n) {
+    B200MF_MG_CASE(2) B200MF_MG_CASE(3) B200MF_MG_CASE(4) B200MF_MG_CASE(5)
+    B200MF_MG_CASE(6) B200MF_MG_CASE(7) B200MF_MG_CASE(8) B200MF_MG_CASE(9)
+  }
+#undef B200MF_MG_CASE
+  set_error("unsupported degree");
+  return B200MF_ERR_INVALID;
+}
+
+template <typename Number>
+static int mg_prolongate(const Mg &mg, int to_level, Number *dst, const Number *src, cudaStream_t st) {
+  int rc = mg_transfer<Number>(mg, to_level, true, dst, src, st);
+  if (rc != B200MF_OK) return rc;
   // dofs constrained on the fine level (Dirichlet) stay zero
-  return set_constrained_impl(*f.s, dst, 0.0, st);
+  return set_constrained_impl(*mg.levels[to_level].s, dst, 0.0, st);
 }
 
 template <typename Number>
 static int mg_restrict_and_add(const Mg &mg, int from_level, Number *dst, const Number *src, cudaStream_t st) {
-  const MgLevel &f = mg.levels[from_level], &c = mg.levels[from_level - 1];
-  const size_t smem = mg_smem_bytes<Number>(mg);
-  const unsigned grid = (unsigned)std::min<uint64_t>(c.s->n_cells, 148ull * 8);
-  if (mg.dim == 3)
-    mg_restrict_kernel<Number, 3><<<grid, kMgThreads, smem, st>>>(dst, src, (const Number *)f.inv_valence, c.s->d_l2g,
-                                                                  f.s->d_l2g, f.d_child, (const Number *)mg.d_P, mg.n,
-                                                                  c.s->n_cells);
-  else
-    mg_restrict_kernel<Number, 2><<<grid, kMgThreads, smem, st>>>(dst, src, (const Number *)f.inv_valence, c.s->d_l2g,
-                                                                  f.s->d_l2g, f.d_child, (const Number *)mg.d_P, mg.n,
-                                                                  c.s->n_cells);
-  count_launch();
-  B200MF_CUDA_CHECK(cudaGetLastError());
-  return B200MF_OK;
+  return mg_transfer<Number>(mg, from_level, false, dst, src, st);
 }
 
 // Multigrid::level_v_step (multigrid.templates.h:112-171); sol/defect of the finest level may be the
@@ -301,16 +335,6 @@ static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
   B200MF_CUDA_CHECK(cudaMalloc(&mg.d_P, Pn.size() * sizeof(Number)));
   B200MF_CUDA_CHECK(cudaMemcpyAsync(mg.d_P, Pn.data(), Pn.size() * sizeof(Number), cudaMemcpyHostToDevice, st));
   B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
-  const size_t smem = mg_smem_bytes<Number>(mg);
-  if (smem > 48 * 1024) {
-    if (mg.dim == 3) {
-      B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_prolongate_kernel<Number, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_restrict_kernel<Number, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
-      B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_prolongate_kernel<Number, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_restrict_kernel<Number, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-  }
   const int nl = (int)mg.levels.size();
   for (int l = 0; l < nl; ++l) {
     MgLevel &L = mg.levels[l];
