@@ -17,6 +17,10 @@
 //       (lac/solver_cg.h:600-760 generic IterationWorker): the UNMODIFIED SolverCG runs on it, every
 //       operation being one b200mf_vec_* kernel (lac/vector_operations_internal.h:2140-2660).
 //   b200::dealii_adapter::DiagonalPreconditioner<Number>   DiagonalMatrix::vmult (lac/diagonal_matrix.h:435)
+//   b200::dealii_adapter::PreconditionMG<dim, LevelNumber>
+//       step-37's PreconditionMG / Multigrid / MGTransferMatrixFree / Chebyshev smoothers from a DoFHandler
+//       with distribute_mg_dofs() + MGConstrainedDoFs, one V-cycle per vmult on the device
+//       (examples/step37_dealii.cc)
 //
 // This image's deal.II has no MPI and Kokkos::Serial only, so LinearAlgebra::distributed::Vector<Number,
 // MemorySpace::Default> lives in host memory there; on a CUDA-enabled deal.II its get_values() is a
@@ -39,9 +43,12 @@
 #include <deal.II/matrix_free/hanging_nodes_internal.h>
 #include <deal.II/matrix_free/shape_info.h>
 
+#include <deal.II/multigrid/mg_constrained_dofs.h>
+
 #include <cuda_runtime_api.h>
 
 #include <functional>
+#include <map>
 #include <memory>
 
 #include "b200mf_portable.hpp"
@@ -163,6 +170,13 @@ public:
   struct AdditionalData : Base::AdditionalData {
     // Portable::MatrixFree::AdditionalData::mapping_update_flags is not needed: the engine derives
     // JxW / inverse Jacobians itself (compressed for Cartesian / affine cells)
+    //
+    // MatrixFree::AdditionalData::mg_level (matrix_free/matrix_free.h: "mg_level"): work on the cells and the
+    // level dofs (DoFHandler::distribute_mg_dofs) of one multigrid level instead of the active cells
+    unsigned int mg_level = dealii::numbers::invalid_unsigned_int;
+    // the CPU MatrixFree's treatment of constrained dofs (MatrixFreeOperators::Base::vmult): they are not read
+    // by the cell loop and their rows are the identity; Portable::MatrixFree (false) reads them
+    bool eliminate_constrained_dofs = false;
   };
 
   void reinit(const dealii::Mapping<dim> &mapping, const dealii::DoFHandler<dim> &dof_handler,
@@ -181,7 +195,10 @@ public:
     const std::shared_ptr<const Utilities::MPI::Partitioner> no_partitioner; // one process
 
     const auto &tria = dof_handler.get_triangulation();
-    n_cells_ = tria.n_active_cells();
+    const bool on_level = additional_data.mg_level != numbers::invalid_unsigned_int;
+    const unsigned int level = additional_data.mg_level;
+    n_cells_ = on_level ? tria.n_cells(level) : tria.n_active_cells();
+    const types::global_dof_index n_dofs = on_level ? dof_handler.n_dofs(level) : dof_handler.n_dofs();
     // d-linear geometry (MappingQ on cells without a curved manifold): hand over the vertices, the
     // engine classifies Cartesian / affine / general cells and compresses; else the arrays PMF stores
     bool flat = dynamic_cast<const MappingQ<dim> *>(&mapping) != nullptr;
@@ -198,14 +215,31 @@ public:
                             update_quadrature_points | (flat ? update_default : (update_inverse_jacobians | update_JxW_values)));
     std::vector<types::global_dof_index> local_dof_indices(dofs_per_cell), lexicographic(dofs_per_cell);
     std::size_t c = 0;
-    for (const auto &cell : dof_handler.active_cell_iterators()) {
-      cell->get_dof_indices(local_dof_indices);
-      for (unsigned int i = 0; i < dofs_per_cell; ++i) lexicographic[i] = local_dof_indices[lexicographic_inv[i]];
-      internal::MatrixFreeFunctions::ConstraintKinds kinds = internal::MatrixFreeFunctions::ConstraintKinds::unconstrained;
-      const ArrayView<internal::MatrixFreeFunctions::ConstraintKinds> view(&kinds, 1);
-      hanging_nodes.setup_constraints(cell, no_partitioner, {lexicographic_inv}, lexicographic, view);
-      mask[c] = static_cast<std::uint16_t>(kinds);
+    // one body for active cells and for the cells of a level (level cells: no hanging-node masks)
+    std::vector<typename Triangulation<dim>::cell_iterator> cells;
+    if (on_level)
+      for (const auto &cell : tria.cell_iterators_on_level(level)) cells.push_back(cell);
+    else
+      for (const auto &cell : tria.active_cell_iterators()) cells.push_back(cell);
+    for (const auto &cell : cells) {
+      if (on_level) {
+        const typename DoFHandler<dim>::level_cell_iterator level_cell(&tria, cell->level(), cell->index(), &dof_handler);
+        level_cell->get_mg_dof_indices(local_dof_indices);
+        for (unsigned int i = 0; i < dofs_per_cell; ++i) lexicographic[i] = local_dof_indices[lexicographic_inv[i]];
+      } else {
+        const typename DoFHandler<dim>::active_cell_iterator active(&tria, cell->level(), cell->index(), &dof_handler);
+        active->get_dof_indices(local_dof_indices);
+        for (unsigned int i = 0; i < dofs_per_cell; ++i) lexicographic[i] = local_dof_indices[lexicographic_inv[i]];
+        internal::MatrixFreeFunctions::ConstraintKinds kinds = internal::MatrixFreeFunctions::ConstraintKinds::unconstrained;
+        const ArrayView<internal::MatrixFreeFunctions::ConstraintKinds> view(&kinds, 1);
+        hanging_nodes.setup_constraints(active, no_partitioner, {lexicographic_inv}, lexicographic, view);
+        mask[c] = static_cast<std::uint16_t>(kinds);
+      }
       for (unsigned int i = 0; i < dofs_per_cell; ++i) l2g[c * dofs_per_cell + i] = lexicographic[i];
+      if (additional_data.eliminate_constrained_dofs)
+        for (unsigned int i = 0; i < dofs_per_cell; ++i)
+          if (constraints.is_constrained(lexicographic[i])) l2g[c * dofs_per_cell + i] |= B200MF_L2G_CONSTRAINED;
+      cell_index_[std::make_pair(cell->level(), cell->index())] = c;
       fe_values.reinit(cell);
       for (unsigned int q = 0; q < nq; ++q)
         for (unsigned int d = 0; d < dim; ++d) q_points_[(c * nq + q) * dim + d] = fe_values.quadrature_point(q)[d];
@@ -224,7 +258,7 @@ public:
       ++c;
     }
     std::vector<std::uint32_t> constrained;
-    for (types::global_dof_index i = 0; i < dof_handler.n_dofs(); ++i)
+    for (types::global_dof_index i = 0; i < n_dofs; ++i)
       if (constraints.is_constrained(i)) constrained.push_back(i);
     bool any_mask = false;
     for (auto m : mask) any_mask = any_mask || m != 0;
@@ -232,7 +266,7 @@ public:
     ReinitData d;
     d.degree = degree;
     d.n_cells = n_cells_;
-    d.n_owned_dofs = dof_handler.n_dofs();
+    d.n_owned_dofs = n_dofs;
     d.local_to_global = l2g.data();
     d.constraint_mask = any_mask ? mask.data() : nullptr;
     if (flat) d.cell_vertices = vertices.data();
@@ -241,8 +275,12 @@ public:
     d.n_constrained_dofs = constrained.size();
     Base::reinit(d, additional_data);
     n_q_ = nq;
-    partitioner_ = std::make_shared<Utilities::MPI::Partitioner>(dof_handler.n_dofs());
+    partitioner_ = std::make_shared<Utilities::MPI::Partitioner>(n_dofs);
   }
+
+  // position of a cell (level, index) in this object's cell order
+  std::size_t cell_position(int level, int index) const { return cell_index_.at(std::make_pair(level, index)); }
+  std::size_t n_cells() const { return n_cells_; }
 
   void initialize_dof_vector(Vector<Number> &vec) const { vec.reinit(this->n_local_dofs()); }
   const std::shared_ptr<const dealii::Utilities::MPI::Partitioner> &get_vector_partitioner() const { return partitioner_; }
@@ -262,8 +300,107 @@ public:
 private:
   std::size_t n_cells_ = 0;
   unsigned int n_q_ = 0;
+  std::map<std::pair<int, int>, std::size_t> cell_index_;
   std::vector<double> q_points_;
   std::shared_ptr<const dealii::Utilities::MPI::Partitioner> partitioner_;
+};
+
+// ------------------------------------------------------------------------------------------
+// PreconditionMG + Multigrid + MGTransferMatrixFree + mg::SmootherRelaxation<PreconditionChebyshev> +
+// MGCoarseGridApplySmoother of step-37 (examples/step-37/step-37.cc:950-1060) in one object on the device:
+//   reinit(mapping, dof_handler, mg_constrained_dofs, quad, coefficient)   levels 0 .. n_global_levels-1 from
+//                               DoFHandler::distribute_mg_dofs + MGConstrainedDoFs::get_boundary_indices
+//   vmult(dst, src)             one V-cycle (PreconditionMG::vmult), usable as the preconditioner of deal.II's
+//                               own SolverCG on dealii_adapter::Vector
+// LevelNumber = float under a double CG is step-37's configuration.
+template <int dim, typename LevelNumber>
+class PreconditionMG {
+public:
+  struct AdditionalData {
+    unsigned int smoother_degree = 5;       // PreconditionChebyshev::AdditionalData of step-37.cc:965-975
+    double smoothing_range = 15.;
+    unsigned int eig_cg_n_iterations = 10;
+    double coarse_tolerance = 1e-3;         // level 0: smoothing_range = 1e-3, degree = invalid_unsigned_int
+  };
+  PreconditionMG() = default;
+  PreconditionMG(const PreconditionMG &) = delete;
+  ~PreconditionMG() { clear(); }
+  void clear() {
+    if (mg_) b200mf_mg_destroy(mg_);
+    mg_ = nullptr;
+    levels_.clear();
+    coefficients_.clear();
+  }
+
+  void reinit(const dealii::Mapping<dim> &mapping, const dealii::DoFHandler<dim> &dof_handler,
+              const dealii::MGConstrainedDoFs &mg_constrained_dofs, const dealii::Quadrature<1> &quad,
+              const std::function<LevelNumber(const dealii::Point<dim> &)> &coefficient = {},
+              const AdditionalData &data = AdditionalData()) {
+    using namespace dealii;
+    clear();
+    const auto &tria = dof_handler.get_triangulation();
+    const unsigned int n_levels = tria.n_global_levels();
+    std::vector<const b200mf_setup *> setups;
+    std::vector<b200mf_operator> operators;
+    std::vector<std::vector<std::uint32_t>> children(n_levels > 0 ? n_levels - 1 : 0);
+    std::vector<const std::uint32_t *> child_ptrs;
+    for (unsigned int level = 0; level < n_levels; ++level) {
+      AffineConstraints<LevelNumber> level_constraints;
+      for (const types::global_dof_index i : mg_constrained_dofs.get_boundary_indices(level))
+        level_constraints.constrain_dof_to_zero(i);
+      level_constraints.close();
+      typename MatrixFree<dim, LevelNumber>::AdditionalData ad;
+      ad.mg_level = level;
+      ad.eliminate_constrained_dofs = true;
+      levels_.emplace_back(new MatrixFree<dim, LevelNumber>());
+      levels_.back()->reinit(mapping, dof_handler, level_constraints, quad, ad);
+      coefficients_.emplace_back(new Vector<LevelNumber>());
+      if (coefficient) levels_.back()->evaluate_coefficients(coefficient, *coefficients_.back());
+      setups.push_back(levels_.back()->get_setup());
+      operators.push_back(b200mf_operator{coefficient ? coefficients_.back()->get_values() : nullptr, nullptr, 1.0, 0.0});
+    }
+    // the children of every cell of level l, as positions in level l+1's cell order, x fastest
+    // (GeometryInfo<dim>::child_cell_on_face ordering = the lexicographic child numbering of hypercubes)
+    for (unsigned int level = 0; level + 1 < n_levels; ++level) {
+      auto &table = children[level];
+      table.assign(levels_[level]->n_cells() << dim, 0);
+      for (const auto &cell : tria.cell_iterators_on_level(level)) {
+        if (!cell->has_children())
+          throw Exception(B200MF_ERR_UNSUPPORTED, "PreconditionMG: globally refined meshes only (a level cell without children)");
+        const std::size_t c = levels_[level]->cell_position(cell->level(), cell->index());
+        for (unsigned int k = 0; k < GeometryInfo<dim>::max_children_per_cell; ++k)
+          table[(c << dim) + k] = levels_[level + 1]->cell_position(cell->child(k)->level(), cell->child(k)->index());
+      }
+      child_ptrs.push_back(table.data());
+    }
+    b200mf_mg_desc d{};
+    d.n_levels = n_levels;
+    d.levels = setups.data();
+    d.operators = operators.data();
+    d.child_cells = child_ptrs.empty() ? nullptr : child_ptrs.data();
+    d.smoother_degree = data.smoother_degree;
+    d.smoothing_range = data.smoothing_range;
+    d.eig_cg_n_iterations = data.eig_cg_n_iterations;
+    d.coarse_tolerance = data.coarse_tolerance;
+    d.safety_factor = 1.2;
+    check(b200mf_mg_create(&d, &mg_, nullptr));
+  }
+
+  template <typename Number>
+  void vmult(Vector<Number> &dst, const Vector<Number> &src) const {
+    check(b200mf_mg_vcycle(mg_, number_code<Number>(), dst.get_values(), src.get_values(), nullptr));
+  }
+  b200mf_mg_level_info level_info(unsigned int level) const {
+    b200mf_mg_level_info info;
+    check(b200mf_mg_get_level_info(mg_, level, &info));
+    return info;
+  }
+  unsigned int n_levels() const { return levels_.size(); }
+
+private:
+  b200mf_mg *mg_ = nullptr;
+  std::vector<std::unique_ptr<MatrixFree<dim, LevelNumber>>> levels_;
+  std::vector<std::unique_ptr<Vector<LevelNumber>>> coefficients_;
 };
 
 } // namespace dealii_adapter

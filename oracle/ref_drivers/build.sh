@@ -43,11 +43,13 @@ fi
 # deal.II host code driving libb200mf.so; it can only be compiled where deal.II's headers are
 ROOT="$HERE/../.."
 if [ -f "$ROOT/dealii_b200/libb200mf.so" ]; then
-  if [ ! -x "$BIN/step64_b200" ] || [ "$ROOT/examples/step64_dealii.cc" -nt "$BIN/step64_b200" ] || [ "$ROOT/include/b200mf_dealii.hpp" -nt "$BIN/step64_b200" ]; then
-    ( $CXX $FLAGS $INC -I"$ROOT/include" -I/usr/local/cuda/include "$ROOT/examples/step64_dealii.cc" -o "$BIN/step64_b200" \
-        $LINK -L"$ROOT/dealii_b200" -lb200mf -Wl,-rpath,\$ORIGIN/../../../dealii_b200 -L/usr/local/cuda/lib64 -lcudart ) &
-    pids+=($!)
-  fi
+  for ex in step64 step37; do
+    if [ ! -x "$BIN/${ex}_b200" ] || [ "$ROOT/examples/${ex}_dealii.cc" -nt "$BIN/${ex}_b200" ] || [ "$ROOT/include/b200mf_dealii.hpp" -nt "$BIN/${ex}_b200" ]; then
+      ( $CXX $FLAGS $INC -I"$ROOT/include" -I/usr/local/cuda/include "$ROOT/examples/${ex}_dealii.cc" -o "$BIN/${ex}_b200" \
+          $LINK -L"$ROOT/dealii_b200" -lb200mf -Wl,-rpath,\$ORIGIN/../../../dealii_b200 -L/usr/local/cuda/lib64 -lcudart ) &
+      pids+=($!)
+    fi
+  done
 fi
 rc=0
 for p in "${pids[@]:-}"; do [ -z "$p" ] || wait "$p" || rc=1; done
