@@ -73,7 +73,8 @@ class MgDesc(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("levels", C.POINTER(vp)), ("operators", C.POINTER(Operator)),
                 ("child_cells", C.POINTER(vp)), ("smoother_degree", C.c_int32),
                 ("smoothing_range", C.c_double), ("eig_cg_n_iterations", C.c_int32),
-                ("coarse_tolerance", C.c_double), ("safety_factor", C.c_double)]
+                ("coarse_tolerance", C.c_double), ("safety_factor", C.c_double),
+                ("partitioners", C.POINTER(vp))]
 
 
 class MgLevelInfo(C.Structure):
@@ -105,7 +106,7 @@ class PartitionView(C.Structure):
     _fields_ = [("n_global_dofs", u64), ("n_global_cells", u64), ("first_owned_global", u64),
                 ("n_owned", u64), ("n_ghost", u64), ("n_cells_interior", u64),
                 ("rank_offsets", C.POINTER(u64)), ("ghost_global", C.POINTER(u64)),
-                ("lattice_ids", C.POINTER(u64))]
+                ("lattice_ids", C.POINTER(u64)), ("cell_morton_position", C.POINTER(u64))]
 
 
 class AdaptiveDesc(C.Structure):
@@ -177,6 +178,8 @@ SYMBOLS = {
     "b200mf_mg_vcycle": (C.c_int, [vp, C.c_int, vp, vp, vp]),
     "b200mf_mg_cg_solve": (C.c_int, [vp, vp, C.POINTER(Operator), C.c_double, C.c_int, vp, vp,
                                      C.POINTER(SolverResult), vp]),
+    "b200mf_mg_dist_cg_solve": (C.c_int, [vp, vp, vp, C.POINTER(Operator), C.c_double, C.c_int, vp, vp,
+                                          C.POINTER(SolverResult), vp]),
     "b200mf_cg_solve_host": (C.c_int, [vp, C.POINTER(Operator), C.POINTER(SolverDesc), vp, vp,
                                        C.POINTER(SolverResult)]),
     "b200mf_mesh_create": (C.c_int, [C.POINTER(MeshDesc), C.POINTER(vp)]),

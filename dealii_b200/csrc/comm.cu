@@ -578,3 +578,17 @@ int b200mf_dist_cg_solve(const b200mf_setup *h, const b200mf_partitioner *p, con
 }
 
 } // extern "C"
+
+// hooks for the solvers that run on one rank or on a partition alike (solver_impl.cuh, multigrid.cu)
+namespace b200mf {
+int level_vmult(const Setup &s, const b200mf_partitioner *p, const b200mf_operator &op, void *dst, void *src,
+                cudaStream_t st, double *dot_accum) {
+  return p ? dist_vmult_impl(s, *p, op, dst, src, st, dot_accum) : vmult_impl(s, op, dst, src, st, dot_accum);
+}
+int level_allreduce(const b200mf_partitioner *p, double *device_values, int count, cudaStream_t st) {
+  if (!p || p->n_ranks == 1) return B200MF_OK;
+  return b200mf_comm_allreduce_sum(p->comm, device_values, count, st);
+}
+uint64_t level_first_owned(const b200mf_partitioner *p) { return p ? p->first_owned : 0; }
+bool level_is_distributed(const b200mf_partitioner *p) { return p && p->n_ranks > 1; }
+} // namespace b200mf

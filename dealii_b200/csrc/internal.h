@@ -213,6 +213,16 @@ int copy_constrained_impl(const Setup &s, void *dst, const void *src, cudaStream
 int vmult_prepare_impl(const Setup &s, const b200mf_operator &op, void *dst, cudaStream_t st);
 int set_constrained_impl(const Setup &s, void *dst, double value, cudaStream_t st);
 
+// comm.cu: the operator / reductions of a level that may be partitioned over ranks (p == nullptr: one rank)
+} // namespace b200mf
+struct b200mf_partitioner;
+namespace b200mf {
+int level_vmult(const Setup &s, const b200mf_partitioner *p, const b200mf_operator &op, void *dst, void *src,
+                cudaStream_t st, double *dot_accum);
+int level_allreduce(const b200mf_partitioner *p, double *device_values, int count, cudaStream_t st);
+uint64_t level_first_owned(const b200mf_partitioner *p);
+bool level_is_distributed(const b200mf_partitioner *p);
+
 // kernels_dispatch.cu
 int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                      uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,

@@ -504,6 +504,7 @@ int b200mf_mesh_create_partitioned(const b200mf_partition_desc *pd, b200mf_mesh 
     m->n_cells_interior = ni;
     for (uint64_t c : boundary_cells) order[ni++] = c;
   }
+  m->cell_position = order;
   std::vector<uint64_t> lex_lin(npc);
   for (int i = 0; i < npc; ++i) {
     const int a[3] = {i % n, (i / n) % n, i / (n * n)};
@@ -554,6 +555,7 @@ int b200mf_mesh_partition_view_get(const b200mf_mesh *m, b200mf_partition_view *
   v->rank_offsets = m->rank_offsets.data();
   v->ghost_global = m->ghost_global.data();
   v->lattice_ids = m->lattice_ids.empty() ? nullptr : m->lattice_ids.data();
+  v->cell_morton_position = m->cell_position.empty() ? nullptr : m->cell_position.data();
   return B200MF_OK;
 }
 

@@ -16,7 +16,7 @@ struct b200mf_mesh {
   bool partitioned = false;
   uint64_t n_global_dofs = 0, n_global_cells = 0, first_owned = 0, n_owned = 0, n_ghost = 0,
            n_cells_interior = 0;
-  std::vector<uint64_t> rank_offsets, ghost_global, lattice_ids;
+  std::vector<uint64_t> rank_offsets, ghost_global, lattice_ids, cell_position;
   // adaptive meshes (b200mf_mesh_create_adaptive)
   std::vector<uint16_t> cell_mask;
   std::vector<uint32_t> active_index;

@@ -175,6 +175,7 @@ struct MgLevel {
   b200mf_operator op{};
   void *inv_diag = nullptr, *sol = nullptr, *defect = nullptr, *t = nullptr, *inv_valence = nullptr;
   uint32_t *d_child = nullptr; // children of the cells of the next coarser level (optional)
+  const b200mf_partitioner *part = nullptr; // the level is partitioned over ranks (vectors carry ghost entries)
   double lmin = 1.0, lmax = 1.0, theta = 1.0, delta = 0.0;
   int degree = 1, eig_cg_iterations = 0;
 };
@@ -244,17 +245,31 @@ static int mg_transfer(const Mg &mg, int fine_level, bool prolongate, Number *ds
   return B200MF_ERR_INVALID;
 }
 
+// On partitioned levels the cells of a rank read the coarse (fine) values of dofs other ranks own: the ghost
+// section of src is filled before the kernel (update_ghost_values) and cleared after it; restriction also
+// sends what it added to coarse ghost entries to their owners (compress(add)).  A rank's fine cells are the
+// children of its own coarse cells, so the kernels themselves stay local.
 template <typename Number>
 static int mg_prolongate(const Mg &mg, int to_level, Number *dst, const Number *src, cudaStream_t st) {
-  int rc = mg_transfer<Number>(mg, to_level, true, dst, src, st);
-  if (rc != B200MF_OK) return rc;
+  const MgLevel &f = mg.levels[to_level], &c = mg.levels[to_level - 1];
+  int rc;
+  if (c.part && (rc = b200mf_update_ghost_values(c.part, const_cast<Number *>(src), st)) != B200MF_OK) return rc;
+  if ((rc = mg_transfer<Number>(mg, to_level, true, dst, src, st)) != B200MF_OK) return rc;
+  if (c.part && (rc = b200mf_zero_out_ghost_values(c.part, const_cast<Number *>(src), st)) != B200MF_OK) return rc;
+  if (f.part && (rc = b200mf_zero_out_ghost_values(f.part, dst, st)) != B200MF_OK) return rc;
   // dofs constrained on the fine level (Dirichlet) stay zero
-  return set_constrained_impl(*mg.levels[to_level].s, dst, 0.0, st);
+  return set_constrained_impl(*f.s, dst, 0.0, st);
 }
 
 template <typename Number>
 static int mg_restrict_and_add(const Mg &mg, int from_level, Number *dst, const Number *src, cudaStream_t st) {
-  return mg_transfer<Number>(mg, from_level, false, dst, src, st);
+  const MgLevel &f = mg.levels[from_level], &c = mg.levels[from_level - 1];
+  int rc;
+  if (f.part && (rc = b200mf_update_ghost_values(f.part, const_cast<Number *>(src), st)) != B200MF_OK) return rc;
+  if ((rc = mg_transfer<Number>(mg, from_level, false, dst, src, st)) != B200MF_OK) return rc;
+  if (f.part && (rc = b200mf_zero_out_ghost_values(f.part, const_cast<Number *>(src), st)) != B200MF_OK) return rc;
+  if (c.part && (rc = b200mf_compress_add(c.part, dst, st)) != B200MF_OK) return rc;
+  return B200MF_OK;
 }
 
 // Multigrid::level_v_step (multigrid.templates.h:112-171); sol/defect of the finest level may be the
@@ -268,6 +283,7 @@ static int mg_level_v_step(Mg &mg, int level, Number *sol, const Number *defect,
   Chebyshev<Number> smoother{s, L.op, (const Number *)L.inv_diag, L.degree};
   smoother.theta = L.theta;
   smoother.delta = L.delta;
+  smoother.part = L.part;
   int rc;
   if (level == 0) {
     rc = smoother.apply(sol, defect, st); // MGCoarseGridApplySmoother
@@ -276,12 +292,12 @@ static int mg_level_v_step(Mg &mg, int level, Number *sol, const Number *defect,
   }
   if ((rc = smoother.apply(sol, defect, st)) != B200MF_OK) return rc; // pre_smooth->apply
   Number *t = (Number *)L.t;
-  if ((rc = vmult_impl(s, L.op, t, sol, st, nullptr)) != B200MF_OK) return rc;
+  if ((rc = level_vmult(s, L.part, L.op, t, sol, st, nullptr)) != B200MF_OK) return rc;
   mg.vmults++;
   sadd2_kernel<Number><<<grid, kVecThreads, 0, st>>>(t, Number(-1), Number(1), defect, n); // t = defect - A sol
   count_launch();
   MgLevel &C = mg.levels[level - 1];
-  B200MF_CUDA_CHECK(cudaMemsetAsync(C.defect, 0, C.s->n_owned * sizeof(Number), st));
+  B200MF_CUDA_CHECK(cudaMemsetAsync(C.defect, 0, (C.s->n_owned + C.s->n_ghost) * sizeof(Number), st));
   if ((rc = mg_restrict_and_add<Number>(mg, level, (Number *)C.defect, t, st)) != B200MF_OK) return rc;
   if ((rc = mg_level_v_step<Number>(mg, level - 1, (Number *)C.sol, (const Number *)C.defect, st)) != B200MF_OK)
     return rc;
@@ -303,8 +319,11 @@ static int mg_vcycle(Mg &mg, Outer *dst, const Outer *src, cudaStream_t st) {
   if (std::is_same<Outer, Number>::value)
     return mg_level_v_step<Number>(mg, top, (Number *)dst, (const Number *)src, st);
   if (!mg.top_in) {
-    B200MF_CUDA_CHECK(cudaMalloc(&mg.top_in, std::max<uint64_t>(n, 1) * sizeof(Number)));
-    B200MF_CUDA_CHECK(cudaMalloc(&mg.top_out, std::max<uint64_t>(n, 1) * sizeof(Number)));
+    const uint64_t bytes = std::max<uint64_t>(n + L.s->n_ghost, 1) * sizeof(Number);
+    B200MF_CUDA_CHECK(cudaMalloc(&mg.top_in, bytes));
+    B200MF_CUDA_CHECK(cudaMalloc(&mg.top_out, bytes));
+    B200MF_CUDA_CHECK(cudaMemsetAsync(mg.top_in, 0, bytes, st));
+    B200MF_CUDA_CHECK(cudaMemsetAsync(mg.top_out, 0, bytes, st));
   }
   mg_convert_kernel<Number, Outer><<<vec_grid(n), kVecThreads, 0, st>>>((Number *)mg.top_in, src, n);
   count_launch();
@@ -339,7 +358,7 @@ static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
   for (int l = 0; l < nl; ++l) {
     MgLevel &L = mg.levels[l];
     Setup &s = *L.s;
-    const uint64_t n = s.n_owned, bytes = std::max<uint64_t>(n, 1) * sizeof(Number);
+    const uint64_t n = s.n_owned, nt = s.n_owned + s.n_ghost, bytes = std::max<uint64_t>(nt, 1) * sizeof(Number);
     for (void **v : {&L.inv_diag, &L.sol, &L.defect, &L.t, &L.inv_valence}) {
       B200MF_CUDA_CHECK(cudaMalloc(v, bytes));
       B200MF_CUDA_CHECK(cudaMemsetAsync(*v, 0, bytes, st));
@@ -348,12 +367,15 @@ static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
     if (rc != B200MF_OK) return rc;
     // inverse diagonal (LaplaceOperator::compute_diagonal + get_matrix_diagonal_inverse; constrained rows 1)
     if ((rc = launch_compute_diagonal(s, L.op, L.inv_diag, st)) != B200MF_OK) return rc;
+    if (L.part && (rc = b200mf_compress_add(L.part, L.inv_diag, st)) != B200MF_OK) return rc;
     if ((rc = set_constrained_impl(s, L.inv_diag, 1.0, st)) != B200MF_OK) return rc;
     mg_invert_kernel<Number><<<vec_grid(n), kVecThreads, 0, st>>>((Number *)L.inv_diag, n);
-    // 1 / (number of cells of this level that hold the dof)
+    // 1 / (number of cells of this level, on all ranks, that hold the dof); ghost entries keep a copy
     const uint64_t entries = s.n_cells * (uint64_t)s.dofs_per_cell;
     mg_valence_kernel<Number><<<vec_grid(entries), kVecThreads, 0, st>>>((Number *)L.inv_valence, s.d_l2g, entries);
+    if (L.part && (rc = b200mf_compress_add(L.part, L.inv_valence, st)) != B200MF_OK) return rc;
     mg_invert_kernel<Number><<<vec_grid(n), kVecThreads, 0, st>>>((Number *)L.inv_valence, n);
+    if (L.part && (rc = b200mf_update_ghost_values(L.part, L.inv_valence, st)) != B200MF_OK) return rc;
     count_launch(3);
     B200MF_CUDA_CHECK(cudaGetLastError());
     if (l > 0 && d.child_cells && d.child_cells[l - 1]) {
@@ -364,11 +386,19 @@ static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
     }
     // smoother parameters (step-37.cc:965-984): level 0 is the Chebyshev "solver"
     const bool coarse = (l == 0);
-    const int eig_its = coarse ? (int)std::min<uint64_t>(n, 1u << 20) : d.eig_cg_n_iterations;
+    // eig_cg_n_iterations = mg_matrices[0].m(): the global size of level 0
+    double n_global = double(n);
+    if (level_is_distributed(L.part)) {
+      B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_scratch + 58, &n_global, sizeof(double), cudaMemcpyHostToDevice, st));
+      if ((rc = level_allreduce(L.part, s.d_scratch + 58, 1, st)) != B200MF_OK) return rc;
+      B200MF_CUDA_CHECK(cudaMemcpyAsync(&n_global, s.d_scratch + 58, sizeof(double), cudaMemcpyDeviceToHost, st));
+      B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const int eig_its = coarse ? (int)std::min<double>(n_global, double(1u << 20)) : d.eig_cg_n_iterations;
     uint64_t extra = 0;
-    if ((rc = estimate_eigenvalues<Number>(s, L.op, (const Number *)L.inv_diag, eig_its, 0,
+    if ((rc = estimate_eigenvalues<Number>(s, L.op, (const Number *)L.inv_diag, eig_its, level_first_owned(L.part),
                                            d.safety_factor > 0 ? d.safety_factor : 1.2, st, L.lmin, L.lmax, extra,
-                                           &L.eig_cg_iterations, /*zero_constrained=*/false)) != B200MF_OK)
+                                           &L.eig_cg_iterations, /*zero_constrained=*/false, L.part)) != B200MF_OK)
       return rc;
     mg.vmults += extra;
     B200MF_REQUIRE(std::isfinite(L.lmin) && std::isfinite(L.lmax) && L.lmin > 0.0 && L.lmax >= L.lmin,
@@ -394,12 +424,13 @@ static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
 }
 
 template <typename Outer, typename Number>
-static int mg_cg_solve_impl(Mg &mg, Setup &sys, const b200mf_operator &op, double tolerance, int max_iterations,
-                            Outer *x, const Outer *b, b200mf_solver_result *result, cudaStream_t st) {
+static int mg_cg_solve_impl(Mg &mg, Setup &sys, const b200mf_partitioner *sys_part, const b200mf_operator &op,
+                            double tolerance, int max_iterations, Outer *x, const Outer *b,
+                            b200mf_solver_result *result, cudaStream_t st) {
   MgPreconditioner<Outer, Number> prec{mg};
   CgOptions opt{tolerance, max_iterations, false, false, 1};
   CgOutcome out;
-  int rc = cg_generic<Outer>(sys, op, x, b, prec, opt, out, st);
+  int rc = cg_generic<Outer>(sys, op, x, b, prec, opt, out, st, sys_part);
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
   if (result) {
@@ -466,7 +497,9 @@ int b200mf_mg_create(const b200mf_mg_desc *d, b200mf_mg **out, void *stream) {
     if (l == 0) { mg.number = s.number; mg.dim = s.dim; mg.n = s.n; }
     B200MF_REQUIRE(s.number == mg.number && s.dim == mg.dim && s.n == mg.n,
                    "all levels must share number type, dimension and degree");
-    B200MF_REQUIRE(s.n_ghost == 0 && !s.any_mask, "multigrid levels are serial meshes without hanging nodes");
+    mg.levels[l].part = d->partitioners ? d->partitioners[l] : nullptr;
+    B200MF_REQUIRE(!s.any_mask, "multigrid levels are meshes without hanging nodes");
+    B200MF_REQUIRE(s.n_ghost == 0 || mg.levels[l].part, "a level with ghost dofs needs its partitioner");
     if (l > 0)
       B200MF_REQUIRE(s.n_cells == (mg.levels[l - 1].s->n_cells << mg.dim),
                      "level l+1 must be level l refined once (2^dim children per cell)");
@@ -524,22 +557,30 @@ int b200mf_mg_vcycle(b200mf_mg *h, int number, void *dst, const void *src, void 
   return mg_vcycle<float, float>(mg, (float *)dst, (const float *)src, st);
 }
 
-int b200mf_mg_cg_solve(b200mf_mg *h, const b200mf_setup *system, const b200mf_operator *op, double tolerance,
-                       int max_iterations, void *x, const void *b, b200mf_solver_result *result, void *stream) {
+int b200mf_mg_dist_cg_solve(b200mf_mg *h, const b200mf_setup *system, const b200mf_partitioner *system_partitioner,
+                            const b200mf_operator *op, double tolerance, int max_iterations, void *x, const void *b,
+                            b200mf_solver_result *result, void *stream) {
   B200MF_REQUIRE(h && system && op && x && b, "null argument");
   Mg &mg = h->impl;
   Setup &sys = const_cast<Setup &>(system->impl);
-  B200MF_REQUIRE(sys.n_owned == mg.levels.back().s->n_owned && sys.n_ghost == 0,
+  B200MF_REQUIRE(sys.n_owned == mg.levels.back().s->n_owned && sys.n_ghost == mg.levels.back().s->n_ghost,
                  "the system operator must live on the finest multigrid level");
+  B200MF_REQUIRE(sys.n_ghost == 0 || system_partitioner, "a system operator with ghost dofs needs its partitioner");
   cudaStream_t st = (cudaStream_t)stream;
+  const b200mf_partitioner *sp = system_partitioner;
   if (sys.number == B200MF_F64) {
     if (mg.number == B200MF_F64)
-      return mg_cg_solve_impl<double, double>(mg, sys, *op, tolerance, max_iterations, (double *)x, (const double *)b, result, st);
-    return mg_cg_solve_impl<double, float>(mg, sys, *op, tolerance, max_iterations, (double *)x, (const double *)b, result, st);
+      return mg_cg_solve_impl<double, double>(mg, sys, sp, *op, tolerance, max_iterations, (double *)x, (const double *)b, result, st);
+    return mg_cg_solve_impl<double, float>(mg, sys, sp, *op, tolerance, max_iterations, (double *)x, (const double *)b, result, st);
   }
   if (mg.number == B200MF_F64)
-    return mg_cg_solve_impl<float, double>(mg, sys, *op, tolerance, max_iterations, (float *)x, (const float *)b, result, st);
-  return mg_cg_solve_impl<float, float>(mg, sys, *op, tolerance, max_iterations, (float *)x, (const float *)b, result, st);
+    return mg_cg_solve_impl<float, double>(mg, sys, sp, *op, tolerance, max_iterations, (float *)x, (const float *)b, result, st);
+  return mg_cg_solve_impl<float, float>(mg, sys, sp, *op, tolerance, max_iterations, (float *)x, (const float *)b, result, st);
+}
+
+int b200mf_mg_cg_solve(b200mf_mg *h, const b200mf_setup *system, const b200mf_operator *op, double tolerance,
+                       int max_iterations, void *x, const void *b, b200mf_solver_result *result, void *stream) {
+  return b200mf_mg_dist_cg_solve(h, system, nullptr, op, tolerance, max_iterations, x, b, result, stream);
 }
 
 } // extern "C"

@@ -231,7 +231,8 @@ static int ensure_work(Setup &s, int count) {
 // Fused CG with diagonal (or no) preconditioner; d == nullptr => PreconditionIdentity.
 template <typename Number>
 static int cg_fused(Setup &s, const b200mf_operator &op, Number *x, const Number *b,
-                    const Number *d, const CgOptions &opt, CgOutcome &out, cudaStream_t st) {
+                    const Number *d, const CgOptions &opt, CgOutcome &out, cudaStream_t st,
+                    const b200mf_partitioner *part = nullptr) {
   int rc = ensure_work(s, 3);
   if (rc != B200MF_OK) return rc;
   Number *r = (Number *)s.d_work[0], *p = (Number *)s.d_work[1], *v = (Number *)s.d_work[2];
@@ -246,16 +247,18 @@ static int cg_fused(Setup &s, const b200mf_operator &op, Number *x, const Number
   // startup(): r = b - A x unless x == 0 (solver_cg.h:640-652)
   dot2_kernel<Number><<<grid, kVecThreads, 0, st>>>(x, x, n, sc + 32);
   count_launch();
+  if ((rc = level_allreduce(part, sc + 32, 1, st)) != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaMemcpyAsync(h, sc + 32, sizeof(double), cudaMemcpyDeviceToHost, st));
   B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
   const bool x_zero = (h[0] == 0.0);
   if (!x_zero) {
-    rc = vmult_impl(s, op, v, x, st, nullptr);
+    rc = level_vmult(s, part, op, v, x, st, nullptr);
     if (rc != B200MF_OK) return rc;
     out.vmults++;
   }
   cg_init_kernel<Number><<<grid, kVecThreads, 0, st>>>(r, p, b, x_zero ? nullptr : v, d, n, sc);
   count_launch();
+  if ((rc = level_allreduce(part, sc + 8 + 1, 2, st)) != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaMemcpyAsync(h, sc + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
   double res = std::sqrt(h[1]);
@@ -271,11 +274,13 @@ static int cg_fused(Setup &s, const b200mf_operator &op, Number *x, const Number
   double eig_beta_alpha = 0.0, alpha = 0.0;
   while (stt == 0) {
     ++it;
-    rc = vmult_impl(s, op, v, p, st, sc + 8 * (it % 3));
+    rc = level_vmult(s, part, op, v, p, st, sc + 8 * (it % 3));
     if (rc != B200MF_OK) return rc;
     out.vmults++;
+    if ((rc = level_allreduce(part, sc + 8 * (it % 3), 1, st)) != B200MF_OK) return rc;
     cg_post_kernel<Number><<<grid, kVecThreads, 0, st>>>(r, v, d, n, sc, it);
     count_launch();
+    if ((rc = level_allreduce(part, sc + 8 * ((it + 1) % 3) + 1, 2, st)) != B200MF_OK) return rc;
     const int every = opt.track_eigenvalues ? 1 : std::max(opt.check_every, 1);
     if (it % every != 0 && it < opt.max_it) {
       // no look at the residual this iteration: keep the device busy
@@ -325,6 +330,7 @@ struct Chebyshev {
   int degree;
   double theta = 1.0, delta = 1.0;
   uint64_t vmults = 0;
+  const b200mf_partitioner *part = nullptr; // the level is partitioned over ranks
   // z = P(rhs); uses work vectors 3 (sol_old) and 4 (t)
   int apply(Number *z, const Number *rhs, cudaStream_t st) {
     const uint64_t n = s.n_owned;
@@ -338,7 +344,7 @@ struct Chebyshev {
       const double rhokp = 1.0 / (2.0 * sigma - rhok);
       const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / delta;
       rhok = rhokp;
-      int rc = vmult_impl(s, op, t, sol, st, nullptr);
+      int rc = level_vmult(s, part, op, t, sol, st, nullptr);
       if (rc != B200MF_OK) return rc;
       vmults++;
       cheb_update_kernel<Number><<<grid, kVecThreads, 0, st>>>(sol_old, sol, rhs, t, d, Number(f1),
@@ -367,7 +373,7 @@ struct Chebyshev {
         f2 = 2.0 * rhokp / delta;
         rhok = rhokp;
       }
-      int rc = vmult_impl(s, op, t, sol, st, nullptr);
+      int rc = level_vmult(s, part, op, t, sol, st, nullptr);
       if (rc != B200MF_OK) return rc;
       vmults++;
       cheb_update_kernel<Number><<<grid, kVecThreads, 0, st>>>(sol_old, sol, rhs, t, d, Number(f1),
@@ -388,7 +394,7 @@ template <typename Number>
 static int estimate_eigenvalues(Setup &s, const b200mf_operator &op, const Number *d, int eig_cg_n_iterations,
                                 uint64_t first_owned_global_index, double safety_factor, cudaStream_t st,
                                 double &lmin, double &lmax, uint64_t &vmults, int *cg_iterations,
-                                bool zero_constrained = true) {
+                                bool zero_constrained = true, const b200mf_partitioner *part = nullptr) {
   lmin = lmax = 1.0;
   if (cg_iterations) *cg_iterations = 0;
   if (eig_cg_n_iterations <= 0) return B200MF_OK;
@@ -397,13 +403,18 @@ static int estimate_eigenvalues(Setup &s, const b200mf_operator &op, const Numbe
   const uint64_t n = s.n_owned;
   const unsigned grid = vec_grid(n);
   Number *t1 = (Number *)s.d_work[4], *sol = (Number *)s.d_work[3];
+  // [56] sum of the entries, [57] number of entries (both summed over the ranks)
+  const double n_local = double(n);
   B200MF_CUDA_CHECK(cudaMemsetAsync(s.d_scratch + 56, 0, sizeof(double), st));
+  B200MF_CUDA_CHECK(cudaMemcpyAsync(s.d_scratch + 57, &n_local, sizeof(double), cudaMemcpyHostToDevice, st));
   B200MF_CUDA_CHECK(cudaMemsetAsync(sol, 0, (s.n_owned + s.n_ghost) * sizeof(Number), st));
+  B200MF_CUDA_CHECK(cudaMemsetAsync(t1, 0, (s.n_owned + s.n_ghost) * sizeof(Number), st));
   initial_guess_kernel<Number><<<grid, kVecThreads, 0, st>>>(t1, first_owned_global_index, n, s.d_scratch + 56);
   count_launch();
-  B200MF_CUDA_CHECK(cudaMemcpyAsync(s.h_pinned, s.d_scratch + 56, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if ((rc = level_allreduce(part, s.d_scratch + 56, 2, st)) != B200MF_OK) return rc;
+  B200MF_CUDA_CHECK(cudaMemcpyAsync(s.h_pinned, s.d_scratch + 56, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
-  const double mean = s.h_pinned[0] / double(n);
+  const double mean = s.h_pinned[0] / s.h_pinned[1];
   shift_kernel<Number><<<grid, kVecThreads, 0, st>>>(t1, Number(-mean), n);
   count_launch();
   // constraints.set_zero(temp_vector1): AdditionalData::constraints -- empty in step-37's smoothers, where
@@ -413,13 +424,14 @@ static int estimate_eigenvalues(Setup &s, const b200mf_operator &op, const Numbe
   B200MF_CUDA_CHECK(cudaMemsetAsync(s.d_scratch + 57, 0, sizeof(double), st));
   dot2_kernel<Number><<<grid, kVecThreads, 0, st>>>(t1, t1, n, s.d_scratch + 57);
   count_launch();
+  if ((rc = level_allreduce(part, s.d_scratch + 57, 1, st)) != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaMemcpyAsync(s.h_pinned, s.d_scratch + 57, sizeof(double), cudaMemcpyDeviceToHost, st));
   B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
   if (s.h_pinned[0] == 0.0) return B200MF_OK;
   CgOptions eopt{1e-10, eig_cg_n_iterations, true, true};
   CgOutcome eout;
   // the Lanczos CG must not clobber t1 (its rhs) nor sol: it uses work 0..2 only
-  if ((rc = cg_fused<Number>(s, op, sol, t1, d, eopt, eout, st)) != B200MF_OK) return rc;
+  if ((rc = cg_fused<Number>(s, op, sol, t1, d, eopt, eout, st, part)) != B200MF_OK) return rc;
   vmults += eout.vmults;
   if (cg_iterations) *cg_iterations = eout.iterations;
   if (!eout.eigenvalues.empty()) {
@@ -434,7 +446,7 @@ static int estimate_eigenvalues(Setup &s, const b200mf_operator &op, const Numbe
 template <typename Number, typename Preconditioner>
 static int cg_generic(Setup &s, const b200mf_operator &op, Number *x, const Number *b,
                       Preconditioner &prec, const CgOptions &opt, CgOutcome &out,
-                      cudaStream_t st) {
+                      cudaStream_t st, const b200mf_partitioner *part = nullptr) {
   int rc = ensure_work(s, 6);
   if (rc != B200MF_OK) return rc;
   Number *r = (Number *)s.d_work[0], *p = (Number *)s.d_work[1], *v = (Number *)s.d_work[2];
@@ -451,6 +463,7 @@ static int cg_generic(Setup &s, const b200mf_operator &op, Number *x, const Numb
     B200MF_CUDA_CHECK(cudaMemsetAsync(sc + 40, 0, sizeof(double), st));
     dot2_kernel<Number><<<grid, kVecThreads, 0, st>>>(a, c, n, sc + 40);
     count_launch();
+    if (int rca = level_allreduce(part, sc + 40, 1, st)) return rca;
     B200MF_CUDA_CHECK(cudaMemcpyAsync(h, sc + 40, sizeof(double), cudaMemcpyDeviceToHost, st));
     B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
     result = h[0];
@@ -460,7 +473,7 @@ static int cg_generic(Setup &s, const b200mf_operator &op, Number *x, const Numb
   if ((rc = dot(x, x, xx)) != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaMemcpyAsync(r, b, n * sizeof(Number), cudaMemcpyDeviceToDevice, st));
   if (xx != 0.0) {
-    if ((rc = vmult_impl(s, op, v, x, st, nullptr)) != B200MF_OK) return rc;
+    if ((rc = level_vmult(s, part, op, v, x, st, nullptr)) != B200MF_OK) return rc;
     out.vmults++;
     sadd2_kernel<Number><<<grid, kVecThreads, 0, st>>>(r, Number(1), Number(-1), v, n);
     count_launch();
@@ -488,14 +501,16 @@ static int cg_generic(Setup &s, const b200mf_operator &op, Number *x, const Numb
       B200MF_CUDA_CHECK(cudaMemcpyAsync(p, z, n * sizeof(Number), cudaMemcpyDeviceToDevice, st));
     }
     B200MF_CUDA_CHECK(cudaMemsetAsync(sc + 48, 0, 2 * sizeof(double), st));
-    if ((rc = vmult_impl(s, op, v, p, st, sc + 48)) != B200MF_OK) return rc;
+    if ((rc = level_vmult(s, part, op, v, p, st, sc + 48)) != B200MF_OK) return rc;
     out.vmults++;
+    if ((rc = level_allreduce(part, sc + 48, 1, st)) != B200MF_OK) return rc;
     B200MF_CUDA_CHECK(cudaMemcpyAsync(h, sc + 48, sizeof(double), cudaMemcpyDeviceToHost, st));
     B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
     const double alpha = rpr / h[0];
     sadd2_kernel<Number><<<grid, kVecThreads, 0, st>>>(x, Number(1), Number(alpha), p, n);
     axpy_dot_kernel<Number><<<grid, kVecThreads, 0, st>>>(r, Number(-alpha), v, n, sc + 49);
     count_launch(2);
+    if ((rc = level_allreduce(part, sc + 49, 1, st)) != B200MF_OK) return rc;
     B200MF_CUDA_CHECK(cudaMemcpyAsync(h, sc + 49, sizeof(double), cudaMemcpyDeviceToHost, st));
     B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
     res = std::sqrt(std::fabs(h[0]));

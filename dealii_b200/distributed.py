@@ -79,6 +79,8 @@ class PartitionedHyperCubeMesh(HyperCubeMesh):
                              if self.n_ghost else np.zeros(0, dtype=np.uint64))
         self.lattice_ids = (np.ctypeslib.as_array(pv.lattice_ids, shape=(self.n_owned + self.n_ghost,)).copy()
                             if want_lattice_ids else None)
+        # position of every local cell in this rank's Morton chunk (cells are ordered [no ghost | rest])
+        self.cell_morton_position = np.ctypeslib.as_array(pv.cell_morton_position, shape=(self.n_cells,)).copy()
 
 
 class AdaptiveHyperCubeMesh(PartitionedHyperCubeMesh):
@@ -435,3 +437,80 @@ def solve_cg(dmf, op, x, b, inverse_diagonal, tolerance, max_iterations, check_e
     if code not in (L.OK, L.ERR_NOCONVERGENCE):
         L.check(code)
     return res.iterations, res.residual, code == L.OK
+
+
+class DistributedGeometricMultigrid:
+    """step-37's multigrid on a partitioned mesh (b200mf_mg_* with per-level partitioners): every rank holds
+    its coarse cell(s) of hyper_rectangle(coarse) refined l times for l = min_level..refinements; the levels'
+    operators, smoothers and transfers exchange ghosts through the C partitioners, the dot products of the
+    outer CG are all-reduced.  Names as in dealii_b200.multigrid.GeometricMultigrid."""
+
+    def __init__(self, dim, degree, refinements, n_ranks, rank, coarse=(1, 1, 1), number="f32", device="cuda:0",
+                 group=None, comm=None, min_level=0, smoother_degree=5, smoothing_range=15.0,
+                 eig_cg_n_iterations=10, coarse_tolerance=1e-3, safety_factor=1.2):
+        import dealii_b200
+        self._lib = L.load()
+        self.comm = comm if comm is not None else Communicator(torch.device(device), group)
+        self.levels, self.level_operators, tables = [], [], []
+        for level in range(min_level, refinements + 1):
+            mesh = PartitionedHyperCubeMesh(dim, degree, level, n_ranks, rank, coarse=coarse, dirichlet_boundary=True,
+                                            mark_constrained_l2g=True, ghost_mode="touched")
+            dmf = DistributedMatrixFree(mesh, number, device, group, comm=self.comm)
+            self.levels.append(dmf)
+            self.level_operators.append(dealii_b200.LaplaceOperator(dmf.mf))
+        for lc, lf in zip(self.levels[:-1], self.levels[1:]):
+            pos_c, pos_f = lc.mesh.cell_morton_position, lf.mesh.cell_morton_position
+            inv_f = np.empty(len(pos_f), dtype=np.int64)
+            inv_f[pos_f.astype(np.int64)] = np.arange(len(pos_f))
+            kids = (pos_c.astype(np.int64)[:, None] << dim) + np.arange(1 << dim)[None, :]
+            tables.append(np.ascontiguousarray(inv_f[kids], dtype=np.uint32))
+        self._tables = tables
+        n = len(self.levels)
+        desc = L.MgDesc()
+        desc.n_levels = n
+        self._setups = (C.c_void_p * n)(*[lv.mf._h for lv in self.levels])
+        self._ops = (L.Operator * n)(*[op.op for op in self.level_operators])
+        self._parts = (C.c_void_p * n)(*[lv.partitioner._h for lv in self.levels])
+        self._children = (C.c_void_p * max(n - 1, 1))(*[t.ctypes.data for t in tables])
+        desc.levels = C.cast(self._setups, C.POINTER(C.c_void_p))
+        desc.operators = C.cast(self._ops, C.POINTER(L.Operator))
+        desc.child_cells = C.cast(self._children, C.POINTER(C.c_void_p)) if n > 1 else None
+        desc.partitioners = C.cast(self._parts, C.POINTER(C.c_void_p))
+        desc.smoother_degree, desc.smoothing_range = smoother_degree, smoothing_range
+        desc.eig_cg_n_iterations, desc.coarse_tolerance = eig_cg_n_iterations, coarse_tolerance
+        desc.safety_factor = safety_factor
+        self._h = C.c_void_p()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(self._lib.b200mf_mg_create(C.byref(desc), C.byref(self._h), st))
+
+    def n_levels(self):
+        return len(self.levels)
+
+    def level_info(self, level):
+        info = L.MgLevelInfo()
+        L.check(self._lib.b200mf_mg_get_level_info(self._h, level, C.byref(info)))
+        return info
+
+    def vmult(self, dst, src):
+        code = L.F64 if src.dtype == torch.float64 else L.F32
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(self._lib.b200mf_mg_vcycle(self._h, code, _ptr(dst), _ptr(src), st))
+
+    def solve(self, system, op, x, b, tolerance, max_steps=100):
+        """SolverCG(SolverControl(max_steps, tolerance)).solve(A, x, b, PreconditionMG) with A = `op` on the
+        DistributedMatrixFree `system` (finest level mesh); returns (iterations, residual, converged)."""
+        res = L.SolverResult()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        code = self._lib.b200mf_mg_dist_cg_solve(self._h, system.mf._h, system.partitioner._h, C.byref(op),
+                                                 float(tolerance), int(max_steps), _ptr(x), _ptr(b), C.byref(res), st)
+        if code not in (L.OK, L.ERR_NOCONVERGENCE):
+            L.check(code)
+        return res.iterations, res.residual, code == L.OK
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self._lib.b200mf_mg_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass

@@ -457,6 +457,12 @@ typedef struct {
   double coarse_tolerance;             /* level 0: smoothing_range < 1 = relative tolerance of the
                                           Chebyshev solver, its degree from the error estimate (1e-3)  */
   double safety_factor;                /* on the largest Lanczos eigenvalue; 0 => 1.2                  */
+  /* NULL (one rank) or n_levels partitioners of the level number type: level l lives on the partitioned
+   * mesh of its setup (vectors = n_owned + n_ghost entries).  Every rank's cells of level l+1 must be the
+   * children of its own cells of level l (b200mf_mesh_create_partitioned with the same coarse cells and
+   * rank count on every level does that); child_cells are then given in local cell indices, from
+   * b200mf_partition_view::cell_morton_position.  All ranks call every b200mf_mg_* function together.   */
+  const b200mf_partitioner *const *partitioners;
 } b200mf_mg_desc;
 
 typedef struct {
@@ -484,6 +490,12 @@ int b200mf_mg_vcycle(b200mf_mg *mg, int number, void *dst, const void *src, void
 int b200mf_mg_cg_solve(b200mf_mg *mg, const b200mf_setup *system, const b200mf_operator *op,
                        double tolerance, int max_iterations, void *x, const void *b,
                        b200mf_solver_result *result, void *stream);
+/* the same on a partitioned mesh: the system operator with its partitioner (of the system's number type);
+ * dot products are all-reduced over the communicator, the V-cycle exchanges ghosts level by level      */
+int b200mf_mg_dist_cg_solve(b200mf_mg *mg, const b200mf_setup *system,
+                            const b200mf_partitioner *system_partitioner, const b200mf_operator *op,
+                            double tolerance, int max_iterations, void *x, const void *b,
+                            b200mf_solver_result *result, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Synthetic mesh + DoF generator (HOST).  Stands in for GridGenerator::hyper_cube +
@@ -549,6 +561,10 @@ typedef struct {
   const uint64_t *rank_offsets;  /* [n_ranks + 1] global range starts of all ranks          */
   const uint64_t *ghost_global;  /* [n_ghost] sorted global indices of the ghost dofs        */
   const uint64_t *lattice_ids;   /* [n_owned + n_ghost] or NULL                             */
+  /* [n_cells] position of every local cell in this rank's Morton chunk (local cells are ordered
+   * [touching no ghost | rest]); the children of the cell at position c are at positions
+   * (c << dim) + k of the mesh refined once more -- the multigrid transfer's child tables        */
+  const uint64_t *cell_morton_position;
 } b200mf_partition_view;
 
 int b200mf_mesh_create_partitioned(const b200mf_partition_desc *desc, b200mf_mesh **out);
