@@ -675,53 +675,61 @@ def run_cg(args, dev, rank, world, coarse, barrier, max_over_ranks, peak):
                             "ms_total_incl_eigenvalue_estimate": best,
                             "note": "SolverCG + PreconditionChebyshev(degree 3, 10 CG iterations for the "
                                     "eigenvalue estimate) through b200mf_cg_solve"}
-    if world == 1 and args.workload == "c2" and args.deformation == 0.0 and not args.no_gmg:
-        out["gmg"] = run_gmg(args, b)
+    if args.workload == "c2" and args.deformation == 0.0 and not args.no_gmg:
+        out["gmg"] = run_gmg(args, dev, rank, world, coarse, barrier, max_over_ranks, dmf.comm)
     return out
 
 
-def run_gmg(args, b_like):
+def run_gmg(args, dev, rank, world, coarse, barrier, max_over_ranks, comm):
     """Time to solution with the geometric multigrid of step-37 on the same problem
     as the converged Jacobi solve: FP64 CG preconditioned by one V-cycle (Chebyshev(5) smoothers on
-    float levels, matrix-free transfer, Chebyshev coarse solver), through b200mf_mg_cg_solve."""
+    float levels, matrix-free transfer, Chebyshev coarse solver), through b200mf_mg_create +
+    b200mf_mg_dist_cg_solve.  On N ranks every rank holds its cube on every level (weak scaling): the
+    iteration count does not grow with N, unlike Jacobi-CG's."""
     import time
     import torch
     import dealii_b200
+    from dealii_b200.distributed import (DistributedGeometricMultigrid, DistributedMatrixFree,
+                                         PartitionedHyperCubeMesh)
     t0 = time.time()
-    mg = dealii_b200.GeometricMultigrid.for_hyper_cube(3, args.degree, args.refinements, number=args.gmg_levels)
+    mg = DistributedGeometricMultigrid(3, args.degree, args.refinements, world, rank, coarse=coarse,
+                                       number=args.gmg_levels, device=dev, comm=comm)
     torch.cuda.synchronize()
     t_setup = time.time() - t0
-    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=args.refinements, dirichlet_boundary=True,
-                                     mark_constrained_l2g=True)
-    mf = dealii_b200.MatrixFree("f64")
-    mf.reinit_from_mesh(mesh)
-    A = dealii_b200.LaplaceOperator(mf)
-    b = mf.initialize_dof_vector()
-    b[:] = 1.0
-    mf.set_constrained_values(0.0, b)
-    tol = args.cg_rel_tol * float(b.norm())
-    best, res = None, None
+    mesh = PartitionedHyperCubeMesh(3, args.degree, args.refinements, world, rank, coarse=coarse,
+                                    dirichlet_boundary=True, mark_constrained_l2g=True, ghost_mode="touched")
+    system = DistributedMatrixFree(mesh, "f64", dev, comm=comm)
+    A = dealii_b200.LaplaceOperator(system.mf)
+    n = mesh.n_owned
+    b = system.initialize_dof_vector()
+    b[:n] = 1.0
+    system.mf.set_constrained_values(0.0, b)
+    scal = torch.tensor([float(torch.dot(b[:n], b[:n]))], device=dev, dtype=torch.float64)
+    comm.allreduce_sum(scal)
+    bnorm = float(scal) ** 0.5
+    tol = args.cg_rel_tol * bnorm
+    best, its, ok = None, 0, False
     for rep in range(2):                      # first solve = warm-up
-        x = mf.initialize_dof_vector()
+        x = system.initialize_dof_vector()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        control = dealii_b200.SolverControl(100, tol)
-        res = dealii_b200.SolverCG(control).solve(A, x, b, mg)
+        its, res, ok = mg.solve(system, A.op, x, b, tol, 100)
         e1.record()
         torch.cuda.synchronize()
-        best = e0.elapsed_time(e1)
+        best = max_over_ranks(e0.elapsed_time(e1))
     # the answer is checked against the operator: ||b - A x|| / ||b||
-    r = mf.initialize_dof_vector()
-    A.vmult(r, x)
-    true_res = float((b - r).norm() / b.norm())
+    r = system.initialize_dof_vector()
+    system.vmult(A.op, r, x)
+    rr = torch.tensor([float(torch.dot(b[:n] - r[:n], b[:n] - r[:n]))], device=dev, dtype=torch.float64)
+    comm.allreduce_sum(rr)
     return {"metric": "cg_gmg_time_to_solution", "levels": mg.n_levels(), "level_number": args.gmg_levels,
-            "n_dofs": mesh.n_dofs, "relative_tolerance": args.cg_rel_tol, "iterations": res.iterations,
-            "seconds": best * 1e-3, "true_relative_residual": true_res,
-            "operator_applications": int(res.operator_applications),
-            "value": mesh.n_dofs / (best * 1e-3) / 1e9, "unit": "GDoF/s (unknowns solved per second)",
+            "n_dofs": mesh.n_global_dofs, "relative_tolerance": args.cg_rel_tol, "iterations": its,
+            "converged": bool(ok), "seconds": best * 1e-3, "true_relative_residual": float(rr) ** 0.5 / bnorm,
+            "value": mesh.n_global_dofs / (best * 1e-3) / 1e9, "unit": "GDoF/s (unknowns solved per second)",
             "setup_seconds_host_incl_level_meshes": t_setup,
             "smoother": "Chebyshev degree 5, range 15, 10 Lanczos iterations (step-37.cc:965-975)",
-            "api": "b200mf_mg_create + b200mf_mg_cg_solve (include/b200mf.h)"}
+            "api": "b200mf_mg_create + b200mf_mg_dist_cg_solve (include/b200mf.h)"}
 
 
 def run_sweep(args):

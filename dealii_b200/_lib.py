@@ -60,7 +60,8 @@ class SolverDesc(C.Structure):
                 ("chebyshev_degree", C.c_int), ("smoothing_range", C.c_double),
                 ("eig_cg_n_iterations", C.c_int), ("safety_factor", C.c_double),
                 ("tolerance", C.c_double), ("max_iterations", C.c_int),
-                ("first_owned_global_index", u64), ("check_every", C.c_int)]
+                ("first_owned_global_index", u64), ("check_every", C.c_int),
+                ("max_eigenvalue", C.c_double)]
 
 
 class SolverResult(C.Structure):

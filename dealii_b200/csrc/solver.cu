@@ -24,6 +24,11 @@ static int solve_impl(Setup &s, const b200mf_operator &op, const b200mf_solver_d
                                            sd.safety_factor > 0 ? sd.safety_factor : 1.2, st, lmin, lmax,
                                            extra_vmults, nullptr)) != B200MF_OK)
       return rc;
+    if (sd.eig_cg_n_iterations <= 0) {
+      // no estimate: AdditionalData::max_eigenvalue and the smoothing range define the interval
+      lmax = sd.max_eigenvalue > 0.0 ? sd.max_eigenvalue : 1.0;
+      lmin = sd.smoothing_range > 0.0 ? lmax / sd.smoothing_range : lmax;
+    }
     const double alpha = sd.smoothing_range > 1.0 ? lmax / sd.smoothing_range
                                                   : std::min(0.9 * lmax, lmin);
     Chebyshev<Number> prec{s, op, d, sd.chebyshev_degree};

@@ -300,6 +300,10 @@ typedef struct {
    * check_every iterations; 0 or 1 = every iteration like SolverControl (lac/solver_control.h). With
    * k > 1 the solve may run up to k - 1 iterations past the tolerance.                           */
   int check_every;
+  /* PreconditionChebyshev::AdditionalData::max_eigenvalue: used when eig_cg_n_iterations == 0 (no Lanczos
+   * estimate): largest eigenvalue = max_eigenvalue (0 => 1), smallest = max_eigenvalue / smoothing_range
+   * (lac/precondition.h:2563-2568)                                                                       */
+  double max_eigenvalue;
 } b200mf_solver_desc;
 
 typedef struct {

@@ -127,3 +127,33 @@ def test_solver_cg_interleave_golden(case):
     assert abs(float(x.norm()) - norm) < 2e-5 * norm   # stopped at 1e-2: +-1 iteration moves the norm
     if control.last_step() == its:
         assert abs(float(x.norm()) - norm) < 1e-7 * norm
+
+
+def test_chebyshev_with_a_prescribed_maximal_eigenvalue():
+    """PreconditionChebyshev::AdditionalData::eig_cg_n_iterations = 0: no Lanczos estimate, the interval is
+    [max_eigenvalue / smoothing_range, max_eigenvalue] (lac/precondition.h:2563-2568).  Handing the estimate
+    of a first solve back as max_eigenvalue must reproduce that solve."""
+    ref = step64.run_cycle(2)
+    mf, A = build(ref)
+    inv_diag = A.compute_diagonal()
+    b = torch.from_numpy(ref["b"]).cuda()
+    tol = 1e-12 * float(np.linalg.norm(ref["b"]))
+    est = dealii_b200.PreconditionChebyshev(degree=4, smoothing_range=12.0, eig_cg_n_iterations=10, preconditioner=inv_diag)
+    x0 = mf.initialize_dof_vector()
+    c0 = dealii_b200.SolverControl(1000, tol)
+    r0 = dealii_b200.SolverCG(c0).solve(A, x0, b, est)
+    fixed = dealii_b200.PreconditionChebyshev(degree=4, smoothing_range=12.0, eig_cg_n_iterations=0,
+                                              preconditioner=inv_diag, max_eigenvalue=r0.chebyshev_max_eigenvalue)
+    x1 = mf.initialize_dof_vector()
+    c1 = dealii_b200.SolverControl(1000, tol)
+    r1 = dealii_b200.SolverCG(c1).solve(A, x1, b, fixed)
+    assert r1.chebyshev_max_eigenvalue == pytest.approx(r0.chebyshev_max_eigenvalue, rel=1e-14)
+    assert r1.chebyshev_min_eigenvalue == pytest.approx(r0.chebyshev_max_eigenvalue / 12.0, rel=1e-14)
+    assert c1.last_step() == c0.last_step()
+    assert torch.allclose(x1, x0, rtol=1e-9, atol=1e-12 * float(x0.abs().max()))
+    # a different interval is a different preconditioner
+    other = dealii_b200.PreconditionChebyshev(degree=4, smoothing_range=12.0, eig_cg_n_iterations=0,
+                                              preconditioner=inv_diag, max_eigenvalue=3.0 * r0.chebyshev_max_eigenvalue)
+    c2 = dealii_b200.SolverControl(1000, tol)
+    dealii_b200.SolverCG(c2).solve(A, mf.initialize_dof_vector(), b, other)
+    assert c2.last_step() != c0.last_step()
