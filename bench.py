@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-chebyshev", action="store_true")
     ap.add_argument("--no-renumbered", action="store_true")
     ap.add_argument("--no-gmg", action="store_true")
+    ap.add_argument("--gmg-reference-refinements", type=int, default=5,
+                    help="size of the same-problem comparison with the reference's own CPU multigrid (oracle/_ref ref_gmg)")
     ap.add_argument("--gmg-levels", default="f32", choices=["f32", "f64"],
                     help="number type of the multigrid levels under the FP64 CG (step-37 uses float)")
     ap.add_argument("--cg-rel-tol", type=float, default=1e-6)
@@ -723,13 +725,63 @@ def run_gmg(args, dev, rank, world, coarse, barrier, max_over_ranks, comm):
     system.vmult(A.op, r, x)
     rr = torch.tensor([float(torch.dot(b[:n] - r[:n], b[:n] - r[:n]))], device=dev, dtype=torch.float64)
     comm.allreduce_sum(rr)
+    same_size = None
+    if world == 1 and not args.no_cpu_baseline:
+        same_size = gmg_reference_comparison(args, dev)
     return {"metric": "cg_gmg_time_to_solution", "levels": mg.n_levels(), "level_number": args.gmg_levels,
+            "same_problem_on_the_reference": same_size,
             "n_dofs": mesh.n_global_dofs, "relative_tolerance": args.cg_rel_tol, "iterations": its,
             "converged": bool(ok), "seconds": best * 1e-3, "true_relative_residual": float(rr) ** 0.5 / bnorm,
             "value": mesh.n_global_dofs / (best * 1e-3) / 1e9, "unit": "GDoF/s (unknowns solved per second)",
             "setup_seconds_host_incl_level_meshes": t_setup,
             "smoother": "Chebyshev degree 5, range 15, 10 Lanczos iterations (step-37.cc:965-975)",
             "api": "b200mf_mg_create + b200mf_mg_dist_cg_solve (include/b200mf.h)"}
+
+
+def gmg_reference_comparison(args, dev):
+    """The reference's own matrix-free multigrid (step-37's classes in the unmodified deal.II of oracle/_ref,
+    driver oracle/ref_drivers/ref_gmg.cc, one host core: this build has neither MPI nor TBB) and the engine on
+    the same, smaller problem with the same tolerance."""
+    import subprocess
+    import tempfile
+    import torch
+    import dealii_b200
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", f"ref_gmg_q{args.degree}")
+    r = args.gmg_reference_refinements
+    if not os.path.exists(exe) or r > args.refinements:
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        try:
+            out = subprocess.run([exe, "3", str(r), args.gmg_levels, "constant", tmp, "timing"], capture_output=True,
+                                 text=True, timeout=600)
+            ref = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        except Exception as e:            # the checker is optional for the product's own numbers
+            return {"unavailable": repr(e)[:200]}
+    mg = dealii_b200.GeometricMultigrid.for_hyper_cube(3, args.degree, r, number=args.gmg_levels)
+    mesh = dealii_b200.HyperCubeMesh(3, args.degree, refinements=r, dirichlet_boundary=True, mark_constrained_l2g=True)
+    mf = dealii_b200.MatrixFree("f64", dev)
+    mf.reinit_from_mesh(mesh)
+    A = dealii_b200.LaplaceOperator(mf)
+    plain = dealii_b200.MatrixFree("f64", dev)
+    plain.reinit_from_mesh(dealii_b200.HyperCubeMesh(3, args.degree, refinements=r))
+    b = mf.initialize_dof_vector()
+    one = torch.ones_like(b)
+    dealii_b200.MatrixFreeOperator(plain, grad_constant=0.0, mass_constant=1.0).vmult(b, one)   # rhs_i = (phi_i, 1)
+    mf.set_constrained_values(0.0, b)
+    best = None
+    for rep in range(3):
+        x = mf.initialize_dof_vector()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        control = dealii_b200.SolverControl(100, ref["relative_tolerance"] * float(b.norm()))
+        dealii_b200.SolverCG(control).solve(A, x, b, mg)
+        e1.record()
+        torch.cuda.synchronize()
+        best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+    return {"n_dofs": ref["n_dofs"], "refinements": r, "relative_tolerance": ref["relative_tolerance"],
+            "reference": {"seconds": ref["seconds"], "iterations": ref["iterations"], "cores": ref["cores"],
+                          "what": "deal.II SolverCG + PreconditionMG (MGTransferMatrixFree, PreconditionChebyshev) on the host"},
+            "engine": {"seconds": best * 1e-3, "iterations": control.last_step()}}
 
 
 def run_sweep(args):

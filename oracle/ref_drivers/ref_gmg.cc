@@ -13,7 +13,8 @@
 // eigenvalue estimates, one application of the transfer operators, one V-cycle, the CG iteration count
 // and the solution.
 //
-// usage: ref_gmg <dim> <refinements> <levels: f32|f64> <coef: constant|step37> <outdir>
+// usage: ref_gmg <dim> <refinements> <levels: f32|f64> <coef: constant|step37> <outdir> [timing]
+// (timing: no array dumps, relative tolerance 1e-6, best of two solves, one JSON line on stdout)
 // Compiled once per degree (-DREF_DEGREE=k).  Output: raw little-endian arrays + manifest.json.
 #include <deal.II/base/quadrature_lib.h>
 
@@ -46,6 +47,7 @@
 
 #include <deal.II/numerics/vector_tools.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -61,7 +63,8 @@ struct Dump
 {
   std::string   dir;
   std::ofstream manifest;
-  bool          first = true;
+  bool          first  = true;
+  bool          arrays = true; // false: scalars only (timing runs on meshes too large to dump)
   explicit Dump(const std::string &d)
     : dir(d)
     , manifest(d + "/manifest.json")
@@ -90,6 +93,8 @@ struct Dump
   void
   array(const std::string &k, const std::vector<T> &v, const char *dtype)
   {
+    if (!arrays)
+      return;
     std::ofstream f(dir + "/" + k + ".bin", std::ios::binary);
     f.write(reinterpret_cast<const char *>(v.data()), sizeof(T) * v.size());
     key(k);
@@ -99,6 +104,8 @@ struct Dump
   void
   vector(const std::string &k, const LinearAlgebra::distributed::Vector<Number> &v)
   {
+    if (!arrays)
+      return;
     std::vector<double> out(v.size());
     for (unsigned int i = 0; i < v.size(); ++i)
       out[i] = v.local_element(i);
@@ -141,7 +148,7 @@ evaluate_coefficient(const MatrixFree<dim, Number> &mf, const bool variable)
 
 template <int dim, int degree, typename LevelNumber>
 void
-run(const unsigned int refinements, const bool variable, const std::string &outdir)
+run(const unsigned int refinements, const bool variable, const std::string &outdir, const bool timing)
 {
   using SystemVector = LinearAlgebra::distributed::Vector<double>;
   using LevelVector  = LinearAlgebra::distributed::Vector<LevelNumber>;
@@ -149,6 +156,7 @@ run(const unsigned int refinements, const bool variable, const std::string &outd
   using LevelMatrix  = MatrixFreeOperators::LaplaceOperator<dim, degree, degree + 1, 1, LevelVector>;
 
   Dump dump(outdir);
+  dump.arrays = !timing;
   Triangulation<dim> tria(Triangulation<dim>::limit_level_difference_at_vertices);
   GridGenerator::hyper_cube(tria, 0., 1.);
   tria.refine_global(refinements);
@@ -208,6 +216,7 @@ run(const unsigned int refinements, const bool variable, const std::string &outd
       // mesh generator on the mesh of that level)
       std::vector<std::uint32_t>           l2g;
       std::vector<types::global_dof_index> idx(fe.n_dofs_per_cell());
+      if (!timing)
       for (const auto &cell : dof_handler.mg_cell_iterators_on_level(level))
         {
           cell->get_mg_dof_indices(idx);
@@ -308,11 +317,25 @@ run(const unsigned int refinements, const bool variable, const std::string &outd
   preconditioner.vmult(z, rhs);
   dump.vector("vcycle_of_rhs", z);
 
-  SolverControl          control(100, 1e-12 * rhs.l2_norm());
+  const double           rel_tol = timing ? 1e-6 : 1e-12; // timing runs use bench.py's --cg-rel-tol default
+  SolverControl          control(100, rel_tol * rhs.l2_norm());
   SolverCG<SystemVector> cg(control);
-  constraints.set_zero(solution);
-  cg.solve(system_matrix, solution, rhs, preconditioner);
+  double                 best_seconds = 1e300;
+  for (unsigned int rep = 0; rep < (timing ? 2u : 1u); ++rep)
+    {
+      solution = 0;
+      constraints.set_zero(solution);
+      const auto t0 = std::chrono::steady_clock::now();
+      cg.solve(system_matrix, solution, rhs, preconditioner);
+      best_seconds = std::min(best_seconds, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
   constraints.distribute(solution);
+  dump.scalar("solve_seconds", best_seconds);
+  if (timing)
+    std::printf("{\"ref_gmg\": true, \"dim\": %d, \"degree\": %d, \"refinements\": %u, \"n_dofs\": %u, \"levels\": \"%s\", "
+                "\"relative_tolerance\": %g, \"iterations\": %u, \"seconds\": %.6f, \"cores\": 1}\n",
+                dim, degree, refinements, (unsigned)dof_handler.n_dofs(), sizeof(LevelNumber) == 4 ? "f32" : "f64", rel_tol,
+                control.last_step(), best_seconds);
   dump.scalar("cg_iterations", control.last_step());
   dump.scalar("cg_residual", control.last_value());
   dump.scalar("rhs_l2", rhs.l2_norm());
@@ -336,10 +359,11 @@ main(int argc, char **argv)
   const bool         f32         = std::string(argv[3]) == "f32";
   const bool         variable    = std::string(argv[4]) == "step37";
   const std::string  outdir      = argv[5];
+  const bool         timing      = argc > 6 && std::string(argv[6]) == "timing";
   constexpr int      degree      = REF_DEGREE;
   if (dim == 2)
-    f32 ? run<2, degree, float>(refinements, variable, outdir) : run<2, degree, double>(refinements, variable, outdir);
+    f32 ? run<2, degree, float>(refinements, variable, outdir, timing) : run<2, degree, double>(refinements, variable, outdir, timing);
   else
-    f32 ? run<3, degree, float>(refinements, variable, outdir) : run<3, degree, double>(refinements, variable, outdir);
+    f32 ? run<3, degree, float>(refinements, variable, outdir, timing) : run<3, degree, double>(refinements, variable, outdir, timing);
   return 0;
 }

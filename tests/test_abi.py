@@ -60,11 +60,11 @@ def test_no_cpu_fallback():
     assert rc == L.ERR_CUDA and b"no CPU fallback" in L.load().b200mf_last_error()
 
 
-def _build_cxx_example(tmp_path):
+def _build_cxx_example(tmp_path, name="step64_like"):
     import subprocess
-    exe = tmp_path / "step64_like"
+    exe = tmp_path / name
     subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
-                           os.path.join(ROOT, "examples", "step64_like.cc"), "-L", os.path.join(ROOT, "dealii_b200"),
+                           os.path.join(ROOT, "examples", name + ".cc"), "-L", os.path.join(ROOT, "dealii_b200"),
                            "-lb200mf", "-L/usr/local/cuda/lib64", "-lcudart", "-o", str(exe)])
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "dealii_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     return subprocess.run([str(exe)], env=env, capture_output=True, text=True)
@@ -83,3 +83,12 @@ def test_cxx_shim_step64_like_runs(tmp_path):
     r = _build_cxx_example(tmp_path)
     assert r.returncode == 0, r.stderr
     assert "Solved in" in r.stdout and "15625 DoFs" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cxx_multigrid_over_the_c_abi(tmp_path):
+    """examples/step37_like.cc: step-37's solver (CG + V-cycle, FP32 levels) from a C++ host that only includes
+    b200mf.h -- mesh levels, setups, b200mf_mg_create, b200mf_mg_cg_solve."""
+    r = _build_cxx_example(tmp_path, "step37_like")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "35937 DoFs: CG + multigrid converged in" in r.stdout and "level 4" in r.stdout
