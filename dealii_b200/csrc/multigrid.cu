@@ -186,6 +186,18 @@ struct Mg {
   void *d_P = nullptr;
   uint64_t vmults = 0;
   void *top_in = nullptr, *top_out = nullptr; // conversion buffers for callers of the other number type
+  // CUDA graphs of the V-cycle, one per (dst, src) pair it was called with (the CG calls it with the same two
+  // work vectors every iteration): the coarse levels are launch-bound, a replay has no launch gaps
+  struct Graph {
+    const void *dst = nullptr, *src = nullptr;
+    int calls = 0;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0, vmults = 0;
+  };
+  std::vector<Graph> graphs;
+  bool graph_enabled = false;
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_in = nullptr, graph_out = nullptr;
 };
 
 template <typename Number>
@@ -312,7 +324,55 @@ static int mg_level_v_step(Mg &mg, int level, Number *sol, const Number *defect,
 
 // PreconditionMG::vmult for vectors of type Outer (converted to the level number when different)
 template <typename Outer, typename Number>
+static int mg_vcycle_eager(Mg &mg, Outer *dst, const Outer *src, cudaStream_t st);
+
+// The first call with a (dst, src) pair runs eagerly (it also warms every lazily initialised piece), the second
+// is captured on the multigrid's own stream into a graph, later ones replay it.  The caller's stream is ordered
+// before and after the replay with two events.  Anything unexpected while capturing switches graphs off.
+template <typename Outer, typename Number>
 static int mg_vcycle(Mg &mg, Outer *dst, const Outer *src, cudaStream_t st) {
+  if (!mg.graph_enabled) return mg_vcycle_eager<Outer, Number>(mg, dst, src, st);
+  Mg::Graph *g = nullptr;
+  for (auto &e : mg.graphs)
+    if (e.dst == dst && e.src == src) g = &e;
+  if (!g) {
+    if (mg.graphs.size() >= 4) return mg_vcycle_eager<Outer, Number>(mg, dst, src, st);
+    mg.graphs.emplace_back();
+    g = &mg.graphs.back();
+    g->dst = dst;
+    g->src = src;
+  }
+  if (++g->calls == 1) return mg_vcycle_eager<Outer, Number>(mg, dst, src, st);
+  if (!g->exec) {
+    const uint64_t launches_before = g_launch_count.load(), vmults_before = mg.vmults;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(mg.graph_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    const int rc = ok ? mg_vcycle_eager<Outer, Number>(mg, dst, src, mg.graph_stream) : B200MF_ERR_CUDA;
+    if (ok) ok = cudaStreamEndCapture(mg.graph_stream, &graph) == cudaSuccess && graph != nullptr;
+    ok = ok && rc == B200MF_OK && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    g->launches = g_launch_count.load() - launches_before;
+    g->vmults = mg.vmults - vmults_before;
+    if (!ok) {
+      cudaGetLastError(); // clear the capture error; nothing ran
+      mg.graph_enabled = false;
+      g->exec = nullptr;
+      return mg_vcycle_eager<Outer, Number>(mg, dst, src, st);
+    }
+  } else {
+    count_launch(g->launches);
+    mg.vmults += g->vmults;
+  }
+  B200MF_CUDA_CHECK(cudaEventRecord(mg.graph_in, st));
+  B200MF_CUDA_CHECK(cudaStreamWaitEvent(mg.graph_stream, mg.graph_in, 0));
+  B200MF_CUDA_CHECK(cudaGraphLaunch(g->exec, mg.graph_stream));
+  B200MF_CUDA_CHECK(cudaEventRecord(mg.graph_out, mg.graph_stream));
+  B200MF_CUDA_CHECK(cudaStreamWaitEvent(st, mg.graph_out, 0));
+  return B200MF_OK;
+}
+
+template <typename Outer, typename Number>
+static int mg_vcycle_eager(Mg &mg, Outer *dst, const Outer *src, cudaStream_t st) {
   const int top = (int)mg.levels.size() - 1;
   MgLevel &L = mg.levels[top];
   const uint64_t n = L.s->n_owned;
@@ -451,6 +511,11 @@ static int mg_cg_solve_impl(Mg &mg, Setup &sys, const b200mf_partitioner *sys_pa
 }
 
 static void mg_free(Mg &mg) {
+  for (auto &g : mg.graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (mg.graph_stream) cudaStreamDestroy(mg.graph_stream);
+  if (mg.graph_in) cudaEventDestroy(mg.graph_in);
+  if (mg.graph_out) cudaEventDestroy(mg.graph_out);
   for (MgLevel &L : mg.levels) {
     for (void *v : {L.inv_diag, L.sol, L.defect, L.t, L.inv_valence}) cudaFree(v);
     cudaFree(L.d_child);
@@ -508,6 +573,16 @@ int b200mf_mg_create(const b200mf_mg_desc *d, b200mf_mg **out, void *stream) {
   B200MF_MG_DISPATCH(mg.number, rc = mg_setup_levels<T>(mg, *d, (cudaStream_t)stream));
   if (rc != B200MF_OK) return rc;
   B200MF_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  // graphs: one rank only (no NCCL inside a capture), no level on the bulk path (its launch epoch is a kernel
+  // argument), not switched off by B200MF_MG_GRAPH=0
+  mg.graph_enabled = !(getenv("B200MF_MG_GRAPH") && atoi(getenv("B200MF_MG_GRAPH")) == 0);
+  for (const MgLevel &L : mg.levels)
+    if (level_is_distributed(L.part) || (L.s->bulk.ready && L.s->bulk.enabled)) mg.graph_enabled = false;
+  if (mg.graph_enabled) {
+    B200MF_CUDA_CHECK(cudaStreamCreateWithFlags(&mg.graph_stream, cudaStreamNonBlocking));
+    B200MF_CUDA_CHECK(cudaEventCreateWithFlags(&mg.graph_in, cudaEventDisableTiming));
+    B200MF_CUDA_CHECK(cudaEventCreateWithFlags(&mg.graph_out, cudaEventDisableTiming));
+  }
   guard.h = nullptr;
   *out = h;
   return B200MF_OK;
