@@ -13,7 +13,7 @@
 // eigenvalue estimates, one application of the transfer operators, one V-cycle, the CG iteration count
 // and the solution.
 //
-// usage: ref_gmg <dim> <refinements> <levels: f32|f64> <coef: constant|step37> <outdir> [timing]
+// usage: ref_gmg <dim> <refinements> <levels: f32|f64> <coef: constant|step37> <outdir> [timing] [deform=<a>]
 // (timing: no array dumps, relative tolerance 1e-6, best of two solves, one JSON line on stdout)
 // Compiled once per degree (-DREF_DEGREE=k).  Output: raw little-endian arrays + manifest.json.
 #include <deal.II/base/quadrature_lib.h>
@@ -26,6 +26,7 @@
 #include <deal.II/fe/mapping_q1.h>
 
 #include <deal.II/grid/grid_generator.h>
+#include <deal.II/grid/grid_tools.h>
 #include <deal.II/grid/tria.h>
 
 #include <deal.II/lac/affine_constraints.h>
@@ -148,7 +149,8 @@ evaluate_coefficient(const MatrixFree<dim, Number> &mf, const bool variable)
 
 template <int dim, int degree, typename LevelNumber>
 void
-run(const unsigned int refinements, const bool variable, const std::string &outdir, const bool timing)
+run(const unsigned int refinements, const bool variable, const std::string &outdir, const bool timing,
+    const double deformation)
 {
   using SystemVector = LinearAlgebra::distributed::Vector<double>;
   using LevelVector  = LinearAlgebra::distributed::Vector<LevelNumber>;
@@ -160,6 +162,21 @@ run(const unsigned int refinements, const bool variable, const std::string &outd
   Triangulation<dim> tria(Triangulation<dim>::limit_level_difference_at_vertices);
   GridGenerator::hyper_cube(tria, 0., 1.);
   tria.refine_global(refinements);
+  if (deformation != 0.)
+    // the displacement of the engine's mesh generator (B200MF_DEFORM_SINE): every cell of every level becomes a
+    // general cell (the vertices of all levels are moved, like the level meshes the engine generates)
+    GridTools::transform(
+      [deformation](const Point<dim> &p) {
+        double s = deformation;
+        for (unsigned int d = 0; d < dim; ++d)
+          s *= std::sin(numbers::PI * p[d]);
+        Point<dim> q = p;
+        for (unsigned int d = 0; d < dim; ++d)
+          q[d] += s;
+        return q;
+      },
+      tria);
+  dump.scalar("deformation", deformation);
   const FE_Q<dim>    fe(degree);
   const MappingQ1<dim> mapping;
   DoFHandler<dim>    dof_handler(tria);
@@ -359,11 +376,19 @@ main(int argc, char **argv)
   const bool         f32         = std::string(argv[3]) == "f32";
   const bool         variable    = std::string(argv[4]) == "step37";
   const std::string  outdir      = argv[5];
-  const bool         timing      = argc > 6 && std::string(argv[6]) == "timing";
+  bool               timing      = false;
+  double             deformation = 0.;
+  for (int i = 6; i < argc; ++i)
+    {
+      if (std::string(argv[i]) == "timing")
+        timing = true;
+      if (std::string(argv[i]).rfind("deform=", 0) == 0)
+        deformation = std::atof(argv[i] + 7);
+    }
   constexpr int      degree      = REF_DEGREE;
   if (dim == 2)
-    f32 ? run<2, degree, float>(refinements, variable, outdir, timing) : run<2, degree, double>(refinements, variable, outdir, timing);
+    f32 ? run<2, degree, float>(refinements, variable, outdir, timing, deformation) : run<2, degree, double>(refinements, variable, outdir, timing, deformation);
   else
-    f32 ? run<3, degree, float>(refinements, variable, outdir, timing) : run<3, degree, double>(refinements, variable, outdir, timing);
+    f32 ? run<3, degree, float>(refinements, variable, outdir, timing, deformation) : run<3, degree, double>(refinements, variable, outdir, timing, deformation);
   return 0;
 }

@@ -66,14 +66,18 @@ GMG_CASES = {
     "gmg_q2_r5_f32_step37": (3, 2, 5, "f32", "step37", False),
     "gmg_q4_r4_f64": (3, 4, 4, "f64", "constant", False),
     "gmg_d2_q3_r4_f64": (2, 3, 4, "f64", "step37", True),
+    # general cells on every level (the generator's sine displacement)
+    "gmg_q2_r3_f64_deformed": (3, 2, 3, "f64", "step37", True, 0.05),
+    "gmg_q3_r2_f32_deformed": (3, 3, 2, "f32", "constant", True, 0.04),
 }
 
 
 def run_gmg_case(name, spec):
-    dim, degree, ref, number, coef, keep_vectors = spec
+    dim, degree, ref, number, coef, keep_vectors = spec[:6]
+    extra = [f"deform={spec[6]}"] if len(spec) > 6 else []
     exe = os.path.join(BIN, f"ref_gmg_q{degree}")
     with tempfile.TemporaryDirectory() as tmp:
-        subprocess.check_call([exe, str(dim), str(ref), number, coef, tmp])
+        subprocess.check_call([exe, str(dim), str(ref), number, coef, tmp] + extra)
         man = json.load(open(os.path.join(tmp, "manifest.json")))
         out = {}
         for k, v in man.items():

@@ -24,15 +24,17 @@ def step37_coefficient(x):
     return 1.0 / (0.05 + 2.0 * (x * x).sum(axis=1))
 
 
-def hierarchy(dim, degree, refinements, number, variable, **kw):
+def hierarchy(dim, degree, refinements, number, variable, deformation=0.0, **kw):
     from dealii_b200 import GeometricMultigrid
-    return GeometricMultigrid.for_hyper_cube(dim, degree, refinements, number=number,
+    return GeometricMultigrid.for_hyper_cube(dim, degree, refinements, number=number, deformation_amplitude=deformation,
                                              coefficient=step37_coefficient if variable else None, **kw)
 
 
-def system_operator(dim, degree, refinements, variable):
+def system_operator(dim, degree, refinements, variable, deformation=0.0):
     from dealii_b200 import HyperCubeMesh, LaplaceOperator, MatrixFree
-    mesh = HyperCubeMesh(dim, degree, refinements=refinements, dirichlet_boundary=True, mark_constrained_l2g=True)
+    mesh = HyperCubeMesh(dim, degree, refinements=refinements, dirichlet_boundary=True, mark_constrained_l2g=True,
+                         deformation_amplitude=deformation)
+    mesh.deformation = deformation
     mf = MatrixFree("f64")
     mf.reinit_from_mesh(mesh)
     coef = mf.evaluate_coefficients(step37_coefficient) if variable else None
@@ -43,7 +45,8 @@ def unit_rhs(mesh, mf):
     """rhs_i = (phi_i, 1) with constrained entries zero: the mass operator applied to the constant 1."""
     from dealii_b200 import HyperCubeMesh, MatrixFree, MatrixFreeOperator
     plain = MatrixFree("f64")
-    plain.reinit_from_mesh(HyperCubeMesh(mesh.dim, mesh.degree, refinements=int(round(np.log2(mesh.n_cells) / mesh.dim))))
+    plain.reinit_from_mesh(HyperCubeMesh(mesh.dim, mesh.degree, refinements=int(round(np.log2(mesh.n_cells) / mesh.dim)),
+                                         deformation_amplitude=getattr(mesh, "deformation", 0.0)))
     mass = MatrixFreeOperator(plain, grad_constant=0.0, mass_constant=1.0)
     one = torch.ones(mesh.n_dofs, dtype=torch.float64, device="cuda")
     b = torch.zeros_like(one)
@@ -64,6 +67,7 @@ def load(name):
     for k in ("dim", "degree", "refinements", "n_levels", "n_dofs", "cg_iterations", "level_number_bytes"):
         g[k] = int(g[k])
     g["variable"] = bool(int(g["variable_coefficient"]))
+    g["deformation"] = float(g["deformation"]) if "deformation" in g else 0.0
     g["number"] = "f32" if g["level_number_bytes"] == 4 else "f64"
     return g
 
@@ -74,7 +78,7 @@ def test_multigrid_matches_reference(name):
     g = load(name)
     dim, p, r, f32 = g["dim"], g["degree"], g["refinements"], g["number"] == "f32"
     tol = 2e-4 if f32 else 1e-10
-    mg = hierarchy(dim, p, r, g["number"], g["variable"])
+    mg = hierarchy(dim, p, r, g["number"], g["variable"], g["deformation"])
     assert mg.n_levels() == g["n_levels"]
     # ---- level numbering: the engine's mesh of level l is deal.II's level l
     for level in range(g["n_levels"]):
@@ -114,7 +118,7 @@ def test_multigrid_matches_reference(name):
         mg.restrict_and_add(top, dst, src)
         assert_per_entry(dst.cpu().numpy().astype(np.float64), g["restrict_dst"], tol, "restrict_and_add")
     # ---- the solve of step-37: rhs = (phi_i, 1), CG preconditioned by one V-cycle
-    mesh, mf, A = system_operator(dim, p, r, g["variable"])
+    mesh, mf, A = system_operator(dim, p, r, g["variable"], g["deformation"])
     b = unit_rhs(mesh, mf)
     if "rhs" in g:
         assert_per_entry(b.cpu().numpy(), g["rhs"], 1e-12, "rhs")
