@@ -55,17 +55,25 @@ __device__ __forceinline__ uint32_t mg_fine_index(const uint32_t *l2g_f, const u
   return l2g_f[fine * npc + local];
 }
 
+// the 1D embedding matrix travels as a kernel parameter: its entries are constant-bank operands of the
+// fully unrolled line products
+template <typename Number, int n>
+struct MgMatrix {
+  Number P[(2 * n - 1) * n];
+};
+
+// One thread owns one line of a sweep: n inputs from shared memory into registers, the M = 2n-1 outputs of
+// the line with the matrix from the constant bank, M stores (prolongation; restriction is the transpose).
 template <typename Number, int dim, int n>
 __global__ void __launch_bounds__(kMgThreads)
 mg_prolongate_kernel(Number *__restrict__ dst, const Number *__restrict__ src, const uint32_t *__restrict__ l2g_c,
                      const uint32_t *__restrict__ l2g_f, const uint32_t *__restrict__ child,
-                     const Number *__restrict__ P, uint64_t n_coarse_cells) {
+                     const __grid_constant__ MgMatrix<Number, n> mat, uint64_t n_coarse_cells) {
   extern __shared__ __align__(16) unsigned char mg_smem[];
   constexpr int M = 2 * n - 1, nz = dim == 3 ? n : 1, Mz = dim == 3 ? M : 1;
   constexpr int npc = n * n * nz, cap = M * M * Mz;
-  Number *A = reinterpret_cast<Number *>(mg_smem), *B = A + cap, *Ps = B + cap;
+  Number *A = reinterpret_cast<Number *>(mg_smem), *B = A + cap;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int i = tid; i < M * n; i += nthr) Ps[i] = P[i];
   for (uint64_t c = blockIdx.x; c < n_coarse_cells; c += gridDim.x) {
     __syncthreads();
     for (int i = tid; i < npc; i += nthr) {
@@ -73,33 +81,49 @@ mg_prolongate_kernel(Number *__restrict__ dst, const Number *__restrict__ src, c
       A[i] = (idx & B200MF_L2G_CONSTRAINED) ? Number(0) : src[idx];
     }
     __syncthreads();
-    // x: [z][y][i] -> [z][y][X]
-    for (int o = tid; o < n * nz * M; o += nthr) {
-      const int X = o % M, zy = o / M;
-      Number acc = 0;
+    // x: [z][y][i] -> [z][y][X], lines (z, y)
+    for (int line = tid; line < n * nz; line += nthr) {
+      Number u[n];
 #pragma unroll
-      for (int i = 0; i < n; ++i) acc += Ps[X * n + i] * A[zy * n + i];
-      B[o] = acc;
+      for (int i = 0; i < n; ++i) u[i] = A[line * n + i];
+#pragma unroll
+      for (int X = 0; X < M; ++X) {
+        Number acc = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) acc += mat.P[X * n + i] * u[i];
+        B[line * M + X] = acc;
+      }
     }
     __syncthreads();
-    // y: [z][j][X] -> [z][Y][X]
-    for (int o = tid; o < nz * M * M; o += nthr) {
-      const int X = o % M, Y = (o / M) % M, z = o / (M * M);
-      Number acc = 0;
+    // y: [z][j][X] -> [z][Y][X], lines (z, X)
+    for (int line = tid; line < nz * M; line += nthr) {
+      const int X = line % M, z = line / M;
+      Number u[n];
 #pragma unroll
-      for (int j = 0; j < n; ++j) acc += Ps[Y * n + j] * B[(z * n + j) * M + X];
-      A[o] = acc;
+      for (int j = 0; j < n; ++j) u[j] = B[(z * n + j) * M + X];
+#pragma unroll
+      for (int Y = 0; Y < M; ++Y) {
+        Number acc = 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) acc += mat.P[Y * n + j] * u[j];
+        A[(z * M + Y) * M + X] = acc;
+      }
     }
     __syncthreads();
     const Number *R = A;
     if (dim == 3) {
-      // z: [k][Y][X] -> [Z][Y][X]
-      for (int o = tid; o < cap; o += nthr) {
-        const int YX = o % (M * M), Z = o / (M * M);
-        Number acc = 0;
-  #pragma unroll
-      for (int k = 0; k < n; ++k) acc += Ps[Z * n + k] * A[k * M * M + YX];
-        B[o] = acc;
+      // z: [k][Y][X] -> [Z][Y][X], lines (Y, X)
+      for (int line = tid; line < M * M; line += nthr) {
+        Number u[n];
+#pragma unroll
+        for (int k = 0; k < n; ++k) u[k] = A[k * M * M + line];
+#pragma unroll
+        for (int Z = 0; Z < M; ++Z) {
+          Number acc = 0;
+#pragma unroll
+          for (int k = 0; k < n; ++k) acc += mat.P[Z * n + k] * u[k];
+          B[Z * M * M + line] = acc;
+        }
       }
       __syncthreads();
       R = B;
@@ -118,14 +142,13 @@ template <typename Number, int dim, int n>
 __global__ void __launch_bounds__(kMgThreads)
 mg_restrict_kernel(Number *__restrict__ dst, const Number *__restrict__ src, const Number *__restrict__ inv_valence,
                    const uint32_t *__restrict__ l2g_c, const uint32_t *__restrict__ l2g_f,
-                   const uint32_t *__restrict__ child, const Number *__restrict__ P,
+                   const uint32_t *__restrict__ child, const __grid_constant__ MgMatrix<Number, n> mat,
                    uint64_t n_coarse_cells) {
   extern __shared__ __align__(16) unsigned char mg_smem[];
   constexpr int M = 2 * n - 1, nz = dim == 3 ? n : 1, Mz = dim == 3 ? M : 1;
   constexpr int npc = n * n * nz, cap = M * M * Mz;
-  Number *A = reinterpret_cast<Number *>(mg_smem), *B = A + cap, *Ps = B + cap;
+  Number *A = reinterpret_cast<Number *>(mg_smem), *B = A + cap;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int i = tid; i < M * n; i += nthr) Ps[i] = P[i];
   for (uint64_t c = blockIdx.x; c < n_coarse_cells; c += gridDim.x) {
     __syncthreads();
     Number *G = dim == 3 ? B : A;
@@ -139,33 +162,54 @@ mg_restrict_kernel(Number *__restrict__ dst, const Number *__restrict__ src, con
     }
     __syncthreads();
     if (dim == 3) {
-      // z^T: [Z][Y][X] -> [k][Y][X]
-      for (int o = tid; o < n * M * M; o += nthr) {
-        const int YX = o % (M * M), k = o / (M * M);
-        Number acc = 0;
-  #pragma unroll
-      for (int Z = 0; Z < M; ++Z) acc += Ps[Z * n + k] * B[Z * M * M + YX];
-        A[o] = acc;
+      // z^T: [Z][Y][X] -> [k][Y][X], lines (Y, X)
+      for (int line = tid; line < M * M; line += nthr) {
+        Number acc[n];
+#pragma unroll
+        for (int k = 0; k < n; ++k) acc[k] = 0;
+#pragma unroll
+        for (int Z = 0; Z < M; ++Z) {
+          const Number v = B[Z * M * M + line];
+#pragma unroll
+          for (int k = 0; k < n; ++k) acc[k] += mat.P[Z * n + k] * v;
+        }
+#pragma unroll
+        for (int k = 0; k < n; ++k) A[k * M * M + line] = acc[k];
       }
       __syncthreads();
     }
-    // y^T: [k][Y][X] -> [k][j][X]
-    for (int o = tid; o < nz * n * M; o += nthr) {
-      const int X = o % M, j = (o / M) % n, k = o / (M * n);
-      Number acc = 0;
+    // y^T: [k][Y][X] -> [k][j][X], lines (k, X)
+    for (int line = tid; line < nz * M; line += nthr) {
+      const int X = line % M, k = line / M;
+      Number acc[n];
 #pragma unroll
-      for (int Y = 0; Y < M; ++Y) acc += Ps[Y * n + j] * A[(k * M + Y) * M + X];
-      B[o] = acc;
+      for (int j = 0; j < n; ++j) acc[j] = 0;
+#pragma unroll
+      for (int Y = 0; Y < M; ++Y) {
+        const Number v = A[(k * M + Y) * M + X];
+#pragma unroll
+        for (int j = 0; j < n; ++j) acc[j] += mat.P[Y * n + j] * v;
+      }
+#pragma unroll
+      for (int j = 0; j < n; ++j) B[(k * n + j) * M + X] = acc[j];
     }
     __syncthreads();
-    // x^T: [k][j][X] -> [k][j][i], added into the coarse vector
-    for (int o = tid; o < npc; o += nthr) {
-      const int i = o % n, kj = o / n;
-      Number acc = 0;
+    // x^T: [k][j][X] -> [k][j][i], lines (k, j), added into the coarse vector
+    for (int line = tid; line < n * nz; line += nthr) {
+      Number acc[n];
 #pragma unroll
-      for (int X = 0; X < M; ++X) acc += Ps[X * n + i] * B[kj * M + X];
-      const uint32_t idx = l2g_c[c * npc + o];
-      if (!(idx & B200MF_L2G_CONSTRAINED)) atomicAdd(dst + idx, acc);
+      for (int i = 0; i < n; ++i) acc[i] = 0;
+#pragma unroll
+      for (int X = 0; X < M; ++X) {
+        const Number v = B[line * M + X];
+#pragma unroll
+        for (int i = 0; i < n; ++i) acc[i] += mat.P[X * n + i] * v;
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const uint32_t idx = l2g_c[c * npc + line * n + i];
+        if (!(idx & B200MF_L2G_CONSTRAINED)) atomicAdd(dst + idx, acc[i]);
+      }
     }
   }
 }
@@ -183,7 +227,7 @@ struct MgLevel {
 struct Mg {
   int number = 0, dim = 0, n = 0;
   std::vector<MgLevel> levels;
-  void *d_P = nullptr;
+  std::vector<double> P; // 1D embedding matrix [(2n-1)][n]
   uint64_t vmults = 0;
   void *top_in = nullptr, *top_out = nullptr; // conversion buffers for callers of the other number type
   // CUDA graphs of the V-cycle, one per (dst, src) pair it was called with (the CG calls it with the same two
@@ -204,7 +248,7 @@ template <typename Number>
 static size_t mg_smem_bytes(const Mg &mg) {
   const int M = 2 * mg.n - 1;
   size_t cap = (size_t)M * M * (mg.dim == 3 ? M : 1);
-  return (2 * cap + (size_t)M * mg.n) * sizeof(Number);
+  return 2 * cap * sizeof(Number);
 }
 
 // launch shape of the transfer kernels: small CTAs, many per SM (the sweeps of one coarse cell are short and
@@ -230,13 +274,14 @@ static int mg_transfer_launch(const Mg &mg, int fine_level, bool prolongate, Num
     B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_prolongate_kernel<Number, dim, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200MF_CUDA_CHECK(cudaFuncSetAttribute(mg_restrict_kernel<Number, dim, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  MgMatrix<Number, n> mat;
+  for (int i = 0; i < (2 * n - 1) * n; ++i) mat.P[i] = Number(mg.P[i]);
   if (prolongate)
-    mg_prolongate_kernel<Number, dim, n><<<grid, threads, smem, st>>>(dst, src, c.s->d_l2g, f.s->d_l2g, f.d_child,
-                                                                      (const Number *)mg.d_P, c.s->n_cells);
+    mg_prolongate_kernel<Number, dim, n><<<grid, threads, smem, st>>>(dst, src, c.s->d_l2g, f.s->d_l2g, f.d_child, mat,
+                                                                      c.s->n_cells);
   else
     mg_restrict_kernel<Number, dim, n><<<grid, threads, smem, st>>>(dst, src, (const Number *)f.inv_valence, c.s->d_l2g,
-                                                                    f.s->d_l2g, f.d_child, (const Number *)mg.d_P,
-                                                                    c.s->n_cells);
+                                                                    f.s->d_l2g, f.d_child, mat, c.s->n_cells);
   count_launch();
   B200MF_CUDA_CHECK(cudaGetLastError());
   return B200MF_OK;
@@ -408,12 +453,7 @@ struct MgPreconditioner {
 
 template <typename Number>
 static int mg_setup_levels(Mg &mg, const b200mf_mg_desc &d, cudaStream_t st) {
-  std::vector<double> P;
-  build_prolongation_1d(mg.n - 1, P);
-  std::vector<Number> Pn(P.begin(), P.end());
-  B200MF_CUDA_CHECK(cudaMalloc(&mg.d_P, Pn.size() * sizeof(Number)));
-  B200MF_CUDA_CHECK(cudaMemcpyAsync(mg.d_P, Pn.data(), Pn.size() * sizeof(Number), cudaMemcpyHostToDevice, st));
-  B200MF_CUDA_CHECK(cudaStreamSynchronize(st));
+  build_prolongation_1d(mg.n - 1, mg.P);
   const int nl = (int)mg.levels.size();
   for (int l = 0; l < nl; ++l) {
     MgLevel &L = mg.levels[l];
@@ -520,7 +560,6 @@ static void mg_free(Mg &mg) {
     for (void *v : {L.inv_diag, L.sol, L.defect, L.t, L.inv_valence}) cudaFree(v);
     cudaFree(L.d_child);
   }
-  cudaFree(mg.d_P);
   cudaFree(mg.top_in);
   cudaFree(mg.top_out);
 }
