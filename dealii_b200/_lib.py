@@ -173,6 +173,7 @@ SYMBOLS = {
                                   C.POINTER(SolverResult), vp]),
     "b200mf_mg_create": (C.c_int, [C.POINTER(MgDesc), C.POINTER(vp), vp]),
     "b200mf_mg_destroy": (None, [vp]),
+    "b200mf_mg_prolongation_matrix_1d": (C.c_int, [C.c_int, f64p]),
     "b200mf_mg_get_level_info": (C.c_int, [vp, C.c_int, C.POINTER(MgLevelInfo)]),
     "b200mf_mg_prolongate": (C.c_int, [vp, C.c_int, vp, vp, vp]),
     "b200mf_mg_restrict_and_add": (C.c_int, [vp, C.c_int, vp, vp, vp]),

@@ -627,6 +627,14 @@ int b200mf_mg_create(const b200mf_mg_desc *d, b200mf_mg **out, void *stream) {
   return B200MF_OK;
 }
 
+int b200mf_mg_prolongation_matrix_1d(int degree, double *out) {
+  B200MF_REQUIRE(out && degree >= 1 && degree <= 8, "degree must be in 1..8");
+  std::vector<double> P;
+  build_prolongation_1d(degree, P);
+  std::copy(P.begin(), P.end(), out);
+  return B200MF_OK;
+}
+
 void b200mf_mg_destroy(b200mf_mg *h) {
   if (!h) return;
   mg_free(h->impl);

@@ -480,6 +480,10 @@ typedef struct {
 /* Computes the level diagonals, transfer weights and eigenvalue estimates (the lazy
  * estimate_eigenvalues of the reference's smoothers happens here).  The setups must outlive it. */
 int b200mf_mg_create(const b200mf_mg_desc *desc, b200mf_mg **out, void *stream);
+/* HOST: the 1D embedding matrix of FE_Q(degree) the transfer kernels apply per direction,
+ * P[X * (degree+1) + i] = l_i(x_X) for the 2*degree+1 nodes x_X of the two children in the parent's unit cell
+ * (out: (2*degree+1)*(degree+1) doubles).  Needs no device.                                             */
+int b200mf_mg_prolongation_matrix_1d(int degree, double *out);
 void b200mf_mg_destroy(b200mf_mg *mg);
 int b200mf_mg_get_level_info(const b200mf_mg *mg, int level, b200mf_mg_level_info *info);
 /* MGTransferMatrixFree::prolongate(to_level, dst, src): dst (level to_level) = P src (level to_level-1);
