@@ -44,7 +44,8 @@ fi
 ROOT="$HERE/../.."
 if [ -f "$ROOT/dealii_b200/libb200mf.so" ]; then
   for ex in step64 step37; do
-    if [ ! -x "$BIN/${ex}_b200" ] || [ "$ROOT/examples/${ex}_dealii.cc" -nt "$BIN/${ex}_b200" ] || [ "$ROOT/include/b200mf_dealii.hpp" -nt "$BIN/${ex}_b200" ]; then
+    if [ ! -x "$BIN/${ex}_b200" ] || [ "$ROOT/examples/${ex}_dealii.cc" -nt "$BIN/${ex}_b200" ] || [ "$ROOT/include/b200mf_dealii.hpp" -nt "$BIN/${ex}_b200" ] \
+       || [ "$ROOT/include/b200mf_portable.hpp" -nt "$BIN/${ex}_b200" ] || [ "$ROOT/include/b200mf.h" -nt "$BIN/${ex}_b200" ]; then
       ( $CXX $FLAGS $INC -I"$ROOT/include" -I/usr/local/cuda/include "$ROOT/examples/${ex}_dealii.cc" -o "$BIN/${ex}_b200" \
           $LINK -L"$ROOT/dealii_b200" -lb200mf -Wl,-rpath,\$ORIGIN/../../../dealii_b200 -L/usr/local/cuda/lib64 -lcudart ) &
       pids+=($!)
