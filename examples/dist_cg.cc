@@ -8,6 +8,9 @@
 //   -> b200mf_setup_create_from_mesh -> b200mf_comm_create -> b200mf_partitioner_create
 //   -> b200mf_dist_vmult (self-check: the Laplacian annihilates constants across the partition)
 //   -> b200mf_dist_compute_diagonal -> b200mf_dist_cg_solve (Jacobi)
+//   -> the same system with step-37's multigrid as preconditioner: partitioned level meshes 1..r, FP32 level
+//      setups + partitioners, child tables from b200mf_partition_view::cell_morton_position,
+//      b200mf_mg_create -> b200mf_mg_dist_cg_solve
 //
 // Build:  g++ -std=c++17 -Iinclude -I/usr/local/cuda/include examples/dist_cg.cc -Ldealii_b200 -lb200mf
 //             -L/usr/local/cuda/lib64 -lcudart -o dist_cg
@@ -136,6 +139,75 @@ int main() {
   if (rank == 0)
     std::printf("dist_cg: %d ranks, %llu global dofs, 1^T A 1 = %.12e, CG iterations %d, |x| = %.12e, residual %.3e\n", world,
                 (unsigned long long)pv.n_global_dofs, energy, res.iterations, std::sqrt(xx), res.residual);
+
+  // ---- the same solve preconditioned by the geometric multigrid of step-37 on the partitioned hierarchy.
+  // Level 1 (8 cells) is the coarsest level every rank count up to 8 can share; a rank's cells of level l+1 are
+  // the children of its cells of level l (Morton chunks nest), found through cell_morton_position.
+  {
+    const int min_level = 1;
+    std::vector<b200mf_mesh *> level_meshes;
+    std::vector<b200mf_setup *> level_setups;
+    std::vector<b200mf_partitioner *> level_parts;
+    std::vector<b200mf_operator> level_ops;
+    std::vector<std::vector<uint64_t>> positions;
+    for (int level = min_level; level <= refinements; ++level) {
+      b200mf_partition_desc ld = pd;
+      ld.mesh.cells_per_direction = 1 << level;
+      ld.mesh.mark_constrained_l2g = 1; // MatrixFreeOperators::Base: constrained dofs eliminated on the levels
+      b200mf_mesh *lm = nullptr;
+      CHECK(b200mf_mesh_create_partitioned(&ld, &lm));
+      b200mf_partition_view lv;
+      CHECK(b200mf_mesh_partition_view_get(lm, &lv));
+      b200mf_mesh_view lmv;
+      CHECK(b200mf_mesh_view_get(lm, &lmv));
+      b200mf_setup *ls = nullptr;
+      CHECK(b200mf_setup_create_from_mesh(lm, B200MF_F32, &ls));
+      b200mf_partitioner *lp = nullptr;
+      CHECK(b200mf_partitioner_create(comm, lv.rank_offsets, lv.ghost_global, lv.n_ghost, B200MF_F32, &lp));
+      level_meshes.push_back(lm);
+      level_setups.push_back(ls);
+      level_parts.push_back(lp);
+      level_ops.push_back(op);
+      positions.emplace_back(lv.cell_morton_position, lv.cell_morton_position + lmv.n_cells);
+    }
+    std::vector<std::vector<uint32_t>> tables;
+    std::vector<const uint32_t *> table_ptrs;
+    for (size_t l = 0; l + 1 < positions.size(); ++l) {
+      const auto &pc = positions[l], &pf = positions[l + 1];
+      std::vector<uint32_t> inverse(pf.size());
+      for (size_t i = 0; i < pf.size(); ++i) inverse[pf[i]] = (uint32_t)i;
+      std::vector<uint32_t> table(pc.size() * 8);
+      for (size_t i = 0; i < pc.size(); ++i)
+        for (int k = 0; k < 8; ++k) table[i * 8 + k] = inverse[(pc[i] << 3) + k];
+      tables.push_back(std::move(table));
+    }
+    for (const auto &t : tables) table_ptrs.push_back(t.data());
+    b200mf_mg_desc md;
+    std::memset(&md, 0, sizeof md);
+    md.n_levels = (int)level_setups.size();
+    md.levels = level_setups.data();
+    md.operators = level_ops.data();
+    md.child_cells = table_ptrs.empty() ? nullptr : table_ptrs.data();
+    md.partitioners = level_parts.data();
+    md.smoother_degree = 5; md.smoothing_range = 15.0; md.eig_cg_n_iterations = 10; md.coarse_tolerance = 1e-3;
+    b200mf_mg *mg = nullptr;
+    CHECK(b200mf_mg_create(&md, &mg, nullptr));
+    cudaMemset(x, 0, nt * 8);
+    b200mf_solver_result mres;
+    CHECK(b200mf_mg_dist_cg_solve(mg, setup, part, &op, 1e-8 * std::sqrt(bb), 100, x, b, &mres, nullptr));
+    cudaMemset(scal, 0, 64);
+    CHECK(b200mf_vec_dot_device(B200MF_F64, x, x, n, scal, nullptr));
+    CHECK(b200mf_comm_allreduce_sum(comm, scal, 1, nullptr));
+    double xg = 0;
+    cudaMemcpy(&xg, scal, 8, cudaMemcpyDeviceToHost);
+    if (rank == 0)
+      std::printf("dist_gmg: %d ranks, levels %d..%d, CG + multigrid iterations %d, |x| = %.12e, residual %.3e\n", world,
+                  min_level, refinements, mres.iterations, std::sqrt(xg), mres.residual);
+    b200mf_mg_destroy(mg);
+    for (auto *p : level_parts) b200mf_partitioner_destroy(p);
+    for (auto *ls : level_setups) b200mf_setup_destroy(ls);
+    for (auto *lm : level_meshes) b200mf_mesh_destroy(lm);
+  }
   b200mf_partitioner_destroy(part);
   b200mf_setup_destroy(setup);
   b200mf_mesh_destroy(mesh);

@@ -35,7 +35,9 @@ def run(exe, world, tmp):
         assert p.returncode == 0, o + e
     line = [l for l in outs[0][0].splitlines() if l.startswith("dist_cg:")][0]
     m = re.search(r"(\d+) global dofs, 1\^T A 1 = (\S+), CG iterations (\d+), \|x\| = (\S+),", line)
-    return int(m.group(1)), float(m.group(2)), int(m.group(3)), float(m.group(4))
+    line = [l for l in outs[0][0].splitlines() if l.startswith("dist_gmg:")][0]
+    g = re.search(r"CG \+ multigrid iterations (\d+), \|x\| = (\S+),", line)
+    return int(m.group(1)), float(m.group(2)), int(m.group(3)), float(m.group(4)), int(g.group(1)), float(g.group(2))
 
 
 def test_cxx_multi_rank_host():
@@ -43,6 +45,8 @@ def test_cxx_multi_rank_host():
         exe = build(tmp)
         ref = run(exe, 1, tmp)
         assert ref[0] == (4 * 8 + 1) ** 3 and ref[2] > 10
+        # the multigrid-preconditioned solve of the same system: few iterations, the same solution
+        assert ref[4] <= 9 and abs(ref[5] - ref[3]) < 1e-6 * ref[3]
         n_gpus = torch.cuda.device_count()
         for world in (2, 4, 8):
             if n_gpus < world:
@@ -52,3 +56,4 @@ def test_cxx_multi_rank_host():
             assert abs(got[1] - ref[1]) < 1e-10 * abs(ref[1])
             assert abs(got[2] - ref[2]) <= 1
             assert abs(got[3] - ref[3]) < 1e-7 * ref[3]
+            assert abs(got[4] - ref[4]) <= 1 and abs(got[5] - ref[5]) < 1e-7 * ref[5]
