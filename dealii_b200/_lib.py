@@ -61,7 +61,7 @@ class SolverDesc(C.Structure):
                 ("eig_cg_n_iterations", C.c_int), ("safety_factor", C.c_double),
                 ("tolerance", C.c_double), ("max_iterations", C.c_int),
                 ("first_owned_global_index", u64), ("check_every", C.c_int),
-                ("max_eigenvalue", C.c_double)]
+                ("max_eigenvalue", C.c_double), ("eig_keep_constrained_entries", C.c_int)]
 
 
 class SolverResult(C.Structure):

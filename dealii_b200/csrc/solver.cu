@@ -22,7 +22,8 @@ static int solve_impl(Setup &s, const b200mf_operator &op, const b200mf_solver_d
     uint64_t extra_vmults = 0;
     if ((rc = estimate_eigenvalues<Number>(s, op, d, sd.eig_cg_n_iterations, sd.first_owned_global_index,
                                            sd.safety_factor > 0 ? sd.safety_factor : 1.2, st, lmin, lmax,
-                                           extra_vmults, nullptr)) != B200MF_OK)
+                                           extra_vmults, nullptr,
+                                           /*zero_constrained=*/sd.eig_keep_constrained_entries == 0)) != B200MF_OK)
       return rc;
     if (sd.eig_cg_n_iterations <= 0) {
       // no estimate: AdditionalData::max_eigenvalue and the smoothing range define the interval

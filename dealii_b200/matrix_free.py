@@ -311,10 +311,13 @@ class PreconditionChebyshev:
     (lac/precondition.h:2121-2175); the polynomial runs inside b200mf_cg_solve."""
 
     def __init__(self, degree=1, smoothing_range=0.0, eig_cg_n_iterations=8, preconditioner=None,
-                 safety_factor=1.2, max_eigenvalue=1.0):
+                 safety_factor=1.2, max_eigenvalue=1.0, constraints=True):
+        """constraints=True: AdditionalData::constraints = the operator's constraints (their entries of the Lanczos
+        start vector are zeroed); False: the reference's default, an empty AffineConstraints."""
         self.degree, self.smoothing_range = degree, smoothing_range
         self.eig_cg_n_iterations, self.preconditioner = eig_cg_n_iterations, preconditioner
         self.safety_factor, self.max_eigenvalue = safety_factor, max_eigenvalue
+        self.constraints = constraints
 
 
 class SolverControl:
@@ -366,6 +369,7 @@ class SolverCG:
             sd.eig_cg_n_iterations = preconditioner.eig_cg_n_iterations
             sd.safety_factor = preconditioner.safety_factor
             sd.max_eigenvalue = preconditioner.max_eigenvalue
+            sd.eig_keep_constrained_entries = 0 if preconditioner.constraints else 1
         else:
             raise TypeError("unsupported preconditioner")
         res = L.SolverResult()

@@ -278,7 +278,8 @@ int b200mf_vec_add_and_dot(int number, void *y, double a, const void *x, const v
                            double *result_host, void *stream);
 
 /* ------------------------------------------------------------------------------------
- * Solver.  SolverCG<LA::d::Vector>::solve (lac/solver_cg.h:1391) with
+ * Solver (one process: b200mf_dist_cg_solve / b200mf_mg_dist_cg_solve are the multi-rank entry points).
+ * SolverCG<LA::d::Vector>::solve (lac/solver_cg.h:1391) with
  * PreconditionIdentity, DiagonalMatrix (Jacobi, lac/diagonal_matrix.h:435) or
  * PreconditionChebyshev over Jacobi (lac/precondition.h:3928-4121), vector updates and
  * dot products fused around the operator kernel.
@@ -304,6 +305,11 @@ typedef struct {
    * estimate): largest eigenvalue = max_eigenvalue (0 => 1), smallest = max_eigenvalue / smoothing_range
    * (lac/precondition.h:2563-2568)                                                                       */
   double max_eigenvalue;
+  /* The Lanczos start vector of the eigenvalue estimate: 0 = its entries at this setup's constrained dofs are
+   * zeroed, which is what the reference does with AdditionalData::constraints = the problem's constraints
+   * (precondition.h:2494-2500, constraints.set_zero); 1 = they are kept, the reference's default (empty
+   * AdditionalData::constraints, as in step-37's level smoothers).                                        */
+  int eig_keep_constrained_entries;
 } b200mf_solver_desc;
 
 typedef struct {

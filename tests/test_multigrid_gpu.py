@@ -224,3 +224,25 @@ def test_vcycle_is_symmetric_and_iterations_are_mesh_independent(number):
         SolverCG(SolverControl(5000, 1e-10 * float(b.norm()))).solve(A, y, b, A.compute_diagonal())
         assert float((x - y).norm()) < 1e-7 * float(y.norm())
     assert max(its) <= 8 and max(its) - min(its) <= 2, its
+
+
+def test_chebyshev_estimate_with_the_reference_default_constraints():
+    """PreconditionChebyshev in b200mf_cg_solve with AdditionalData::constraints left empty (the reference's
+    default): the Lanczos estimate of the finest-level operator must be the one deal.II's level smoother got."""
+    from dealii_b200 import PreconditionChebyshev, SolverCG, SolverControl
+    g = load("gmg_q2_r2_f64")
+    mesh, mf, A = system_operator(3, 2, 2, False)
+    inv = A.compute_diagonal()
+    b = unit_rhs(mesh, mf)
+    out = {}
+    for constraints in (False, True):
+        prec = PreconditionChebyshev(degree=5, smoothing_range=15.0, eig_cg_n_iterations=10, preconditioner=inv,
+                                     constraints=constraints)
+        x = torch.zeros_like(b)
+        control = SolverControl(200, 1e-10 * float(b.norm()))
+        out[constraints] = SolverCG(control).solve(A, x, b, prec)
+    assert out[False].chebyshev_max_eigenvalue == pytest.approx(float(g["eig_max_2"]), rel=1e-6)
+    assert out[False].chebyshev_min_eigenvalue == pytest.approx(float(g["eig_min_2"]), rel=1e-4)
+    # with the constrained entries zeroed the Krylov space differs: another (valid) estimate
+    assert out[True].chebyshev_max_eigenvalue != out[False].chebyshev_max_eigenvalue
+    assert abs(out[True].iterations - out[False].iterations) <= 2
