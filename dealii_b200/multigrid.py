@@ -41,14 +41,18 @@ class GeometricMultigrid:
 
     @classmethod
     def for_hyper_cube(cls, dim, degree, refinements, number="f64", coefficient=None, min_level=0,
-                       left=0.0, right=1.0, device="cuda:0", deformation_amplitude=0.0, **kwargs):
+                       left=0.0, right=1.0, device="cuda:0", deformation_amplitude=0.0, numbering="default",
+                       **kwargs):
         """Levels min_level..refinements of GridGenerator::hyper_cube + refine_global with homogeneous
         Dirichlet boundary; coefficient(x) (torch, [n_points, dim] -> [n_points]) makes a variable
-        gradient coefficient evaluated at each level's quadrature points (step-37's Coefficient)."""
+        gradient coefficient evaluated at each level's quadrature points (step-37's Coefficient).
+        numbering="lexicographic": every level numbered by DoFRenumbering::lexicographic (the system operator must
+        use the same numbering on the finest mesh); the level operators then run the strided brick kernel."""
         ops = []
         for level in range(min_level, refinements + 1):
             mesh = HyperCubeMesh(dim, degree, refinements=level, left=left, right=right, dirichlet_boundary=True,
-                                 mark_constrained_l2g=True, deformation_amplitude=deformation_amplitude)
+                                 mark_constrained_l2g=True, deformation_amplitude=deformation_amplitude,
+                                 numbering=numbering)
             mf = MatrixFree(number, device)
             mf.reinit_from_mesh(mesh)
             coef = mf.evaluate_coefficients(coefficient) if coefficient is not None else None

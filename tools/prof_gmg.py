@@ -11,8 +11,10 @@ import dealii_b200
 
 degree, refinements = int(sys.argv[1]), int(sys.argv[2])
 levels = sys.argv[3] if len(sys.argv) > 3 else "f32"
-mg = dealii_b200.GeometricMultigrid.for_hyper_cube(3, degree, refinements, number=levels)
-mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements, dirichlet_boundary=True, mark_constrained_l2g=True)
+numbering = sys.argv[4] if len(sys.argv) > 4 else "default"
+mg = dealii_b200.GeometricMultigrid.for_hyper_cube(3, degree, refinements, number=levels, numbering=numbering)
+mesh = dealii_b200.HyperCubeMesh(3, degree, refinements=refinements, dirichlet_boundary=True, mark_constrained_l2g=True,
+                                 numbering=numbering)
 mf = dealii_b200.MatrixFree("f64")
 mf.reinit_from_mesh(mesh)
 A = dealii_b200.LaplaceOperator(mf)
@@ -32,4 +34,4 @@ for rep in range(3):
     dt = time.time() - t0
     if rep == 2:
         torch.cuda.profiler.stop()
-print(f"Q{degree} r{refinements} levels {levels}: {mesh.n_dofs} dofs, {control.last_step()} iterations, {dt * 1e3:.2f} ms")
+print(f"Q{degree} r{refinements} levels {levels} numbering {numbering}: {mesh.n_dofs} dofs, {control.last_step()} iterations, {dt * 1e3:.2f} ms")
