@@ -125,6 +125,7 @@ int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const
                      double *dot_accum, bool dst_zeroed) {
   // Cartesian cells + constant coefficients: whole bricks of cells go to the brick kernel,
   // whatever is left of the range to the per-cell kernels (B200MF_KERNEL=v1|plane: A/B runs)
+  if (s.n_q_1d > s.n) return launch_overint(s, op, dst, src, cell_begin, cell_end, stream, dot_accum, false);
   if (!bricks_enabled(s, op))
     return launch_cells(s, op, dst, src, cell_begin, cell_end, stream, false, dot_accum);
   const uint64_t W = (uint64_t)s.brick_b * s.brick_b * s.brick_b;
@@ -161,6 +162,7 @@ int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const
 
 int launch_compute_diagonal(const Setup &s, const b200mf_operator &op, void *diag,
                             cudaStream_t stream) {
+  if (s.n_q_1d > s.n) return launch_overint(s, op, diag, diag, 0, s.n_cells, stream, nullptr, true);
   return launch_cells(s, op, diag, diag, 0, s.n_cells, stream, true, nullptr);
 }
 
@@ -599,11 +601,22 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   B200MF_REQUIRE(d && out, "null argument");
   B200MF_REQUIRE(d->dim == 2 || d->dim == 3, "dim must be 2 or 3 (got %d)", d->dim);
   B200MF_REQUIRE(d->degree >= 1 && d->degree <= 8, "degree must be in 1..8 (got %d)", d->degree);
-  // same requirement as AssertThrow(n_q_points_1d >= fe_degree+1) in
-  // portable_matrix_free.templates.h:1243, tightened to equality in this release
-  B200MF_REQUIRE(d->n_q_points_1d == d->degree + 1,
-                 "n_q_points_1d must equal degree+1 (got %d for degree %d)", d->n_q_points_1d,
+  // AssertThrow(n_q_points_1d >= fe_degree+1), portable_matrix_free.templates.h:1243.  More points than
+  // fe_degree+1 (over-integration) run the non-collocation kernel of overint.cu
+  B200MF_REQUIRE(d->n_q_points_1d >= d->degree + 1 && d->n_q_points_1d <= 12,
+                 "n_q_points_1d must be in [degree+1, 12] (got %d for degree %d)", d->n_q_points_1d,
                  d->degree);
+  const bool overint = d->n_q_points_1d != d->degree + 1;
+  if (overint) {
+    bool any = false;
+    if (d->constraint_mask)
+      for (uint64_t c = 0; c < d->n_cells && !any; ++c) any = d->constraint_mask[c] != 0;
+    if (any || d->shape_values || d->shape_gradients_collocation || d->quadrature_weights) {
+      set_error("n_q_points_1d > degree+1 is supported on meshes without hanging nodes and with the engine's own "
+                "shape data");
+      return B200MF_ERR_UNSUPPORTED;
+    }
+  }
   B200MF_REQUIRE(d->number == B200MF_F64 || d->number == B200MF_F32, "bad number type");
   B200MF_REQUIRE(d->local_to_global || d->n_cells == 0, "local_to_global is null");
   B200MF_REQUIRE(d->n_owned_dofs + d->n_ghost_dofs < 0x80000000ull,
@@ -628,11 +641,15 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
   } guard{h, d_qp, d_qw};
   Setup &s = h->impl;
   s.dim = d->dim; s.degree = d->degree; s.n = d->degree + 1; s.number = d->number;
+  s.n_q_1d = d->n_q_points_1d;
   s.n_cells = d->n_cells; s.n_owned = d->n_owned_dofs; s.n_ghost = d->n_ghost_dofs;
   s.n_constrained = d->n_constrained_dofs; s.n_cells_interior = d->n_cells_interior;
   s.dofs_per_cell = 1;
   for (int i = 0; i < s.dim; ++i) s.dofs_per_cell *= s.n;
   const int n = s.n, nq = s.dofs_per_cell;
+  const int Q = s.n_q_1d; // quadrature points per direction (= n unless over-integrating)
+  int qpc = 1;            // ... and per cell
+  for (int i = 0; i < s.dim; ++i) qpc *= Q;
   int rc = B200MF_OK;
 #define TRY(x) do { rc = (x); if (rc != B200MF_OK) return rc; } while (0)
 
@@ -704,12 +721,22 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     else                        TRY(upload_converted<float>(&s.d_diag_tables, tb, s, nullptr));
   }
 
+  if (overint) {
+    std::vector<double> S, Dq;
+    build_overint_shape_data(s.degree, Q, S, Dq, s.q_weights, s.q_points_1d);
+    std::vector<double> tb(S);
+    tb.insert(tb.end(), Dq.begin(), Dq.end());
+    tb.insert(tb.end(), s.q_weights.begin(), s.q_weights.end());
+    if (s.number == B200MF_F64) TRY(upload_converted<double>(&s.d_overint_tables, tb, s, nullptr));
+    else                        TRY(upload_converted<float>(&s.d_overint_tables, tb, s, nullptr));
+  }
+
   // --- geometry
-  TRY(dev_alloc_copy<double>(&d_qp, s.q_points_1d.data(), n, s, nullptr));
-  TRY(dev_alloc_copy<double>(&d_qw, s.q_weights.data(), n, s, nullptr));
+  TRY(dev_alloc_copy<double>(&d_qp, s.q_points_1d.data(), Q, s, nullptr));
+  TRY(dev_alloc_copy<double>(&d_qw, s.q_weights.data(), Q, s, nullptr));
   const size_t NS = s.dim * (s.dim + 1) / 2;
   const size_t ns = number_size(s.number);
-  const uint64_t total_q = d->n_cells * (uint64_t)nq;
+  const uint64_t total_q = d->n_cells * (uint64_t)qpc;
   const unsigned blocks = (unsigned)((total_q + 255) / 256);
   if (d->geometry == B200MF_GEOMETRY_Q1_VERTICES) {
     B200MF_REQUIRE(d->cell_vertices || d->n_cells == 0, "cell_vertices is null");
@@ -727,13 +754,13 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
       s.geometry_bytes += total_q * (NS + 1) * ns;
       if (total_q) {
         if (s.dim == 2 && s.number == B200MF_F64)
-          general_geometry_from_vertices<2, double><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+          general_geometry_from_vertices<2, double><<<blocks, 256>>>(d_vert, d_qp, d_qw, Q, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
         else if (s.dim == 2)
-          general_geometry_from_vertices<2, float><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+          general_geometry_from_vertices<2, float><<<blocks, 256>>>(d_vert, d_qp, d_qw, Q, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
         else if (s.number == B200MF_F64)
-          general_geometry_from_vertices<3, double><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+          general_geometry_from_vertices<3, double><<<blocks, 256>>>(d_vert, d_qp, d_qw, Q, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
         else
-          general_geometry_from_vertices<3, float><<<blocks, 256>>>(d_vert, d_qp, d_qw, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+          general_geometry_from_vertices<3, float><<<blocks, 256>>>(d_vert, d_qp, d_qw, Q, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
         count_launch();
       }
       B200MF_CUDA_CHECK(cudaDeviceSynchronize());
@@ -743,7 +770,7 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
       else                        TRY(upload_converted<float>(&s.d_geom_table, table, s, &s.geometry_bytes));
       if (s.n_geom > 1)
         TRY(dev_alloc_copy<uint32_t>(&s.d_geom_id, geom_id.data(), geom_id.size(), s, &s.geometry_bytes));
-      if (s.cell_kind == B200MF_CELLS_CARTESIAN && s.n_geom >= 1 && s.n_geom <= 64 && s.dim == 3) {
+      if (s.cell_kind == B200MF_CELLS_CARTESIAN && s.n_geom >= 1 && s.n_geom <= 64 && s.dim == 3 && !overint) {
         for (int i = 0; i < 4; ++i) s.geom0[i] = table[i];
         s.h_geom_table = table;
         if (s.n_geom > 1) s.h_geom_id = geom_id;
@@ -771,13 +798,13 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
     s.geometry_bytes += total_q * (NS + 1) * ns;
     if (total_q) {
       if (s.dim == 2 && s.number == B200MF_F64)
-        general_geometry_from_jacobians<2, double><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+        general_geometry_from_jacobians<2, double><<<blocks, 256>>>(d_ij, d_jw, qpc, Q, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
       else if (s.dim == 2)
-        general_geometry_from_jacobians<2, float><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+        general_geometry_from_jacobians<2, float><<<blocks, 256>>>(d_ij, d_jw, qpc, Q, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
       else if (s.number == B200MF_F64)
-        general_geometry_from_jacobians<3, double><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
+        general_geometry_from_jacobians<3, double><<<blocks, 256>>>(d_ij, d_jw, qpc, Q, d->n_cells, (double *)s.d_metric, (double *)s.d_jxw);
       else
-        general_geometry_from_jacobians<3, float><<<blocks, 256>>>(d_ij, d_jw, nq, n, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
+        general_geometry_from_jacobians<3, float><<<blocks, 256>>>(d_ij, d_jw, qpc, Q, d->n_cells, (float *)s.d_metric, (float *)s.d_jxw);
       count_launch();
     }
     B200MF_CUDA_CHECK(cudaDeviceSynchronize());
@@ -854,6 +881,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
   Setup *s = &h->impl;
   cudaFree(s->d_l2g); cudaFree(s->d_mask); cudaFree(s->d_geom_id); cudaFree(s->d_geom_table);
   cudaFree(s->d_metric); cudaFree(s->d_jxw); cudaFree(s->d_constrained); cudaFree(s->d_weights);
+  cudaFree(s->d_overint_tables);
   cudaFree(s->d_diag_tables);
   cudaFree(s->d_qpoints); cudaFree(s->d_scratch); cudaFree(s->d_brick_map); cudaFree(s->d_zero_list);
   cudaFree(s->colouring.d_list); cudaFree(s->colouring.d_zero); cudaFree(s->d_brick_strided);
@@ -874,7 +902,7 @@ int b200mf_setup_destroy(b200mf_setup *h) {
 int b200mf_setup_get_info(const b200mf_setup *h, b200mf_setup_info *info) {
   B200MF_REQUIRE(h && info, "null argument");
   const Setup &s = h->impl;
-  info->dim = s.dim; info->degree = s.degree; info->n_q_points_1d = s.n; info->number = s.number;
+  info->dim = s.dim; info->degree = s.degree; info->n_q_points_1d = s.n_q_1d; info->number = s.number;
   info->n_cells = s.n_cells; info->n_owned_dofs = s.n_owned; info->n_ghost_dofs = s.n_ghost;
   info->n_constrained_dofs = s.n_constrained; info->cell_kind = s.cell_kind;
   info->n_distinct_geometries = s.n_geom; info->device_bytes = s.device_bytes;
@@ -889,17 +917,18 @@ int b200mf_get_quadrature_points(const b200mf_setup *h, double *out_host) {
   const Setup &s = h->impl;
   B200MF_REQUIRE(s.has_vertices, "quadrature points need a setup created from Q1 vertices");
   const size_t nvd = (size_t)(1 << s.dim) * s.dim;
-  const uint64_t total_q = s.n_cells * (uint64_t)s.dofs_per_cell;
+  const int Q = s.n_q_1d;
+  const uint64_t total_q = s.n_cells * (uint64_t)(s.dim == 2 ? Q * Q : Q * Q * Q);
   double *d_vert = nullptr, *d_qp = nullptr, *d_out = nullptr;
   B200MF_CUDA_CHECK(cudaMalloc((void **)&d_vert, std::max<size_t>(s.n_cells * nvd, 1) * 8));
-  B200MF_CUDA_CHECK(cudaMalloc((void **)&d_qp, s.n * 8));
+  B200MF_CUDA_CHECK(cudaMalloc((void **)&d_qp, Q * 8));
   B200MF_CUDA_CHECK(cudaMalloc((void **)&d_out, std::max<size_t>(total_q * s.dim, 1) * 8));
   B200MF_CUDA_CHECK(cudaMemcpy(d_vert, s.h_vertices.data(), s.n_cells * nvd * 8, cudaMemcpyHostToDevice));
-  B200MF_CUDA_CHECK(cudaMemcpy(d_qp, s.q_points_1d.data(), s.n * 8, cudaMemcpyHostToDevice));
+  B200MF_CUDA_CHECK(cudaMemcpy(d_qp, s.q_points_1d.data(), Q * 8, cudaMemcpyHostToDevice));
   const unsigned blocks = (unsigned)((total_q + 255) / 256);
   if (total_q) {
-    if (s.dim == 2) quadrature_points_kernel<2><<<blocks, 256>>>(d_vert, d_qp, s.n, s.n_cells, d_out);
-    else            quadrature_points_kernel<3><<<blocks, 256>>>(d_vert, d_qp, s.n, s.n_cells, d_out);
+    if (s.dim == 2) quadrature_points_kernel<2><<<blocks, 256>>>(d_vert, d_qp, Q, s.n_cells, d_out);
+    else            quadrature_points_kernel<3><<<blocks, 256>>>(d_vert, d_qp, Q, s.n_cells, d_out);
     count_launch();
   }
   B200MF_CUDA_CHECK(cudaMemcpy(out_host, d_out, total_q * s.dim * 8, cudaMemcpyDeviceToHost));

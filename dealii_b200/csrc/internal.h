@@ -107,6 +107,10 @@ struct BulkStatsData {
 
 struct Setup {
   int dim = 0, degree = 0, n = 0, number = 0;
+  // quadrature points per direction; > n = over-integration: every cell runs overint.cu, the collocation
+  // kernels (bricks, plane, generic) and their tables are not used
+  int n_q_1d = 0;
+  void *d_overint_tables = nullptr; // S[n][Q] | Dq[Q][Q] | w[Q]  (Number)
   uint64_t n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0, n_cells_interior = 0;
   int dofs_per_cell = 0;
   int cell_kind = B200MF_CELLS_GENERAL;
@@ -223,6 +227,10 @@ int level_allreduce(const b200mf_partitioner *p, double *device_values, int coun
 uint64_t level_first_owned(const b200mf_partitioner *p);
 bool level_is_distributed(const b200mf_partitioner *p);
 
+// overint.cu
+int launch_overint(const Setup &s, const b200mf_operator &op, void *dst, const void *src, uint64_t cell_begin,
+                   uint64_t cell_end, cudaStream_t st, double *dot_accum, bool diagonal);
+
 // kernels_dispatch.cu
 int launch_cell_loop(const Setup &s, const b200mf_operator &op, void *dst, const void *src,
                      uint64_t cell_begin, uint64_t cell_end, cudaStream_t stream,
@@ -260,6 +268,10 @@ void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &q_points, std::vector<double> &subface);
 
 void build_prolongation_1d(int degree, std::vector<double> &P);
+// FE_Q(degree) with QGauss(Q), Q > degree + 1: S[i * Q + q] = l_i(x_q) (Gauss-Lobatto Lagrange basis at the
+// Gauss points), Dq[a * Q + b] = derivative of the Lagrange polynomial of Gauss point a at Gauss point b
+void build_overint_shape_data(int degree, int Q, std::vector<double> &S, std::vector<double> &Dq,
+                              std::vector<double> &weights, std::vector<double> &points);
 
 template <typename Number, int n>
 void fill_shape_data(const Setup &s, ShapeData<Number, n> &out);

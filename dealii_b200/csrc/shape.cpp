@@ -126,6 +126,30 @@ void build_prolongation_1d(int degree, std::vector<double> &P) {
   }
 }
 
+void build_overint_shape_data(int degree, int Q, std::vector<double> &S, std::vector<double> &Dq,
+                              std::vector<double> &weights, std::vector<double> &points) {
+  const int n = degree + 1;
+  std::vector<long double> w;
+  const std::vector<long double> xq = gauss_points(Q, w), xn = gauss_lobatto_points(n);
+  S.assign((size_t)n * Q, 0.0);
+  Dq.assign((size_t)Q * Q, 0.0);
+  weights.resize(Q);
+  points.resize(Q);
+  for (int q = 0; q < Q; ++q) { weights[q] = (double)w[q]; points[q] = (double)xq[q]; }
+  for (int i = 0; i < n; ++i)
+    for (int q = 0; q < Q; ++q) {
+      long double v, d;
+      lagrange(xn, xq[q], i, v, d);
+      S[(size_t)i * Q + q] = (double)v;
+    }
+  for (int a = 0; a < Q; ++a)
+    for (int b = 0; b < Q; ++b) {
+      long double v, d;
+      lagrange(xq, xq[b], a, v, d);
+      Dq[(size_t)a * Q + b] = (double)d;
+    }
+}
+
 void build_fe_q_shape_data(int degree, std::vector<double> &shape_values,
                            std::vector<double> &shape_grad_colloc, std::vector<double> &q_weights,
                            std::vector<double> &q_points, std::vector<double> &subface) {

@@ -160,7 +160,7 @@ class MatrixFree:
         self.dim, self.degree = info.dim, info.degree
         self.n_cells = int(info.n_cells)
         self.n_owned, self.n_ghost = int(info.n_owned_dofs), int(info.n_ghost_dofs)
-        self.n_q_points = (info.degree + 1) ** info.dim
+        self.n_q_points = info.n_q_points_1d ** info.dim
 
     def clear(self):
         if self._h is not None:

@@ -186,8 +186,8 @@ public:
     const FiniteElement<dim> &fe = dof_handler.get_fe();
     const unsigned int degree = fe.degree, n_q_1d = quad.size();
     // same requirement as AssertThrow(n_q_points_1d >= fe_degree + 1), portable_matrix_free.templates.h:1243
-    if (n_q_1d != degree + 1)
-      throw Exception(B200MF_ERR_UNSUPPORTED, "this release requires n_q_points_1d == fe_degree + 1");
+    if (n_q_1d < degree + 1)
+      throw Exception(B200MF_ERR_INVALID, "n_q_points_1d >= fe_degree + 1 is required");
     const unsigned int dofs_per_cell = fe.n_dofs_per_cell(), nq = Utilities::pow(n_q_1d, dim);
     internal::MatrixFreeFunctions::ShapeInfo<Number> shape_info(quad, fe);
     const std::vector<unsigned int> &lexicographic_inv = shape_info.lexicographic_numbering;
@@ -265,6 +265,7 @@ public:
 
     ReinitData d;
     d.degree = degree;
+    d.n_q_points_1d = n_q_1d;
     d.n_cells = n_cells_;
     d.n_owned_dofs = n_dofs;
     d.local_to_global = l2g.data();

@@ -51,6 +51,7 @@ constexpr int number_code() {
 // The arrays Portable::MatrixFree::reinit extracts from (mapping, dof_handler, constraints, quad).
 struct ReinitData {
   int degree = 1;
+  int n_q_points_1d = 0; // 0 => degree + 1
   std::uint64_t n_cells = 0, n_owned_dofs = 0, n_ghost_dofs = 0, n_cells_interior = 0;
   const std::uint32_t *local_to_global = nullptr; // [n_cells][(p+1)^dim], lexicographic, local
   const std::uint16_t *constraint_mask = nullptr; // ConstraintKinds per cell or null
@@ -76,7 +77,8 @@ public:
   void reinit(const ReinitData &d, const AdditionalData & = AdditionalData()) {
     clear();
     b200mf_setup_desc s{};
-    s.dim = dim; s.degree = d.degree; s.n_q_points_1d = d.degree + 1; s.number = number_code<Number>();
+    s.dim = dim; s.degree = d.degree; s.n_q_points_1d = d.n_q_points_1d > 0 ? d.n_q_points_1d : d.degree + 1;
+    s.number = number_code<Number>();
     s.n_cells = d.n_cells; s.n_owned_dofs = d.n_owned_dofs; s.n_ghost_dofs = d.n_ghost_dofs;
     s.local_to_global = d.local_to_global; s.constraint_mask = d.constraint_mask;
     if (d.cell_vertices) { s.geometry = B200MF_GEOMETRY_Q1_VERTICES; s.cell_vertices = d.cell_vertices; }
