@@ -29,6 +29,14 @@ for deg in ${DEGREES:-1 2 3 4 5 6 7 8}; do
     pids+=($!)
   fi
 done
+# over-integrated variants of ref_dump (n_q_points_1d = degree + 1 + extra) for tests/golden/ref_nq
+for spec in ${NQ_SPECS:-2:1 3:1}; do
+  deg=${spec%%:*}; extra=${spec##*:}
+  if [ ! -x "$BIN/ref_dump_q${deg}_nq${extra}" ] || [ "$HERE/ref_dump.cc" -nt "$BIN/ref_dump_q${deg}_nq${extra}" ]; then
+    ( $CXX $FLAGS -DREF_DEGREE=$deg -DREF_NQ_EXTRA=$extra $INC "$HERE/ref_dump.cc" -o "$BIN/ref_dump_q${deg}_nq${extra}" $LINK ) &
+    pids+=($!)
+  fi
+done
 for deg in ${GMG_DEGREES:-1 2 3 4}; do
   if [ ! -x "$BIN/ref_gmg_q$deg" ] || [ "$HERE/ref_gmg.cc" -nt "$BIN/ref_gmg_q$deg" ]; then
     ( $CXX $FLAGS -DREF_DEGREE=$deg $INC "$HERE/ref_gmg.cc" -o "$BIN/ref_gmg_q$deg" $LINK ) &

@@ -55,6 +55,9 @@
 #ifndef REF_DEGREE
 #  error "compile with -DREF_DEGREE=<degree>"
 #endif
+#ifndef REF_NQ_EXTRA
+#  define REF_NQ_EXTRA 0 // quadrature points per direction beyond fe_degree + 1 + REF_NQ_EXTRA (over-integration)
+#endif
 
 using namespace dealii;
 
@@ -131,7 +134,7 @@ public:
     , constraints(constraints)
     , has_mass(op != "laplace")
   {
-    FEEvaluation<dim, degree, degree + 1, 1, double> phi(mf);
+    FEEvaluation<dim, degree, degree + 1 + REF_NQ_EXTRA, 1, double> phi(mf);
     coef.reinit(mf.n_cell_batches(), phi.n_q_points);
     for (unsigned int cell = 0; cell < mf.n_cell_batches(); ++cell)
       {
@@ -173,7 +176,7 @@ private:
   local_apply(const MatrixFree<dim, double> &data, HostVector &dst, const HostVector &src,
               const std::pair<unsigned int, unsigned int> &range) const
   {
-    FEEvaluation<dim, degree, degree + 1, 1, double> phi(data);
+    FEEvaluation<dim, degree, degree + 1 + REF_NQ_EXTRA, 1, double> phi(data);
     for (unsigned int cell = range.first; cell < range.second; ++cell)
       {
         phi.reinit(cell);
@@ -209,7 +212,7 @@ public:
     , has_mass(has_mass)
   {}
   DEAL_II_HOST_DEVICE void
-  operator()(Portable::FEEvaluation<dim, degree, degree + 1, 1, double> *fe_eval, const int q) const
+  operator()(Portable::FEEvaluation<dim, degree, degree + 1 + REF_NQ_EXTRA, 1, double> *fe_eval, const int q) const
   {
     if (has_mass)
       {
@@ -219,7 +222,7 @@ public:
       }
     fe_eval->submit_gradient(fe_eval->get_gradient(q), q);
   }
-  static const unsigned int n_q_points = Utilities::pow(degree + 1, dim);
+  static const unsigned int n_q_points = Utilities::pow(degree + 1 + REF_NQ_EXTRA, dim);
 
 private:
   const double *coef;
@@ -230,7 +233,7 @@ template <int dim, int degree>
 class PmfLocal
 {
 public:
-  static const unsigned int n_q_points = Utilities::pow(degree + 1, dim);
+  static const unsigned int n_q_points = Utilities::pow(degree + 1 + REF_NQ_EXTRA, dim);
   PmfLocal(const double *coef, bool has_mass)
     : coef(coef)
     , has_mass(has_mass)
@@ -239,7 +242,7 @@ public:
   operator()(const typename Portable::MatrixFree<dim, double>::Data *data,
              const Portable::DeviceVector<double> &src, Portable::DeviceVector<double> &dst) const
   {
-    Portable::FEEvaluation<dim, degree, degree + 1, 1, double> fe_eval(data);
+    Portable::FEEvaluation<dim, degree, degree + 1 + REF_NQ_EXTRA, 1, double> fe_eval(data);
     fe_eval.read_dof_values(src);
     fe_eval.evaluate(has_mass ? (EvaluationFlags::values | EvaluationFlags::gradients) :
                                 EvaluationFlags::gradients);
@@ -295,7 +298,7 @@ run(const unsigned int refinements, const std::string &mesh, const std::string &
 
   const FE_Q<dim>  fe(degree);
   const MappingQ1<dim> mapping;
-  const QGauss<1>  quad(degree + 1);
+  const QGauss<1>  quad(degree + 1 + REF_NQ_EXTRA);
   DoFHandler<dim>  dof(tria);
   dof.distribute_dofs(fe);
   if (lexicographic)
@@ -328,7 +331,7 @@ run(const unsigned int refinements, const std::string &mesh, const std::string &
   const auto         data    = pmf.get_data(0);
   const unsigned int n_cells = data.n_cells;
   const unsigned int npc     = fe.n_dofs_per_cell();
-  const unsigned int nq      = Utilities::pow(degree + 1, dim);
+  const unsigned int nq      = Utilities::pow(degree + 1 + REF_NQ_EXTRA, dim);
   if (n_cells != tria.n_active_cells())
     {
       std::fprintf(stderr, "unexpected colouring: %u cells in colour 0 of %u\n", n_cells, tria.n_active_cells());
@@ -470,7 +473,7 @@ run(const unsigned int refinements, const std::string &mesh, const std::string &
   DeviceVector diag(n_dofs);
   {
     PmfQuad<dim, degree> quad_op(coef.get_values(), has_mass);
-    MatrixFreeTools::compute_diagonal<dim, degree, degree + 1, 1, double>(
+    MatrixFreeTools::compute_diagonal<dim, degree, degree + 1 + REF_NQ_EXTRA, 1, double>(
       pmf, diag, quad_op, has_mass ? (EvaluationFlags::values | EvaluationFlags::gradients) : EvaluationFlags::gradients,
       has_mass ? (EvaluationFlags::values | EvaluationFlags::gradients) : EvaluationFlags::gradients);
     Kokkos::fence();

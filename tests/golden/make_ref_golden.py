@@ -71,6 +71,34 @@ GMG_CASES = {
     "gmg_q3_r2_f32_deformed": (3, 3, 2, "f32", "constant", True, 0.04),
 }
 
+# over-integration (n_q_points_1d = degree + 1 + extra; ref_dump compiled with -DREF_NQ_EXTRA=extra):
+# name: (dim, degree, extra, refinements, mesh, op, dirichlet)
+NQ_CASES = {
+    "nq_q2_e1_deformed_var": (3, 2, 1, 2, "deformed", "helmholtz_var", 1),
+    "nq_q3_e1_cartesian": (3, 3, 1, 1, "cartesian", "helmholtz", 0),
+    "nq_d2_q2_e1_cartesian_var": (2, 2, 1, 3, "cartesian", "helmholtz_var", 1),
+}
+OUT_NQ = os.path.join(ROOT, "tests", "golden", "ref_nq")
+
+
+def run_nq_case(name, spec):
+    dim, degree, extra, ref, mesh, op, dirichlet = spec
+    exe = os.path.join(BIN, f"ref_dump_q{degree}_nq{extra}")
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.check_call([exe, str(dim), str(degree), str(ref), mesh, op, str(dirichlet), tmp])
+        man = json.load(open(os.path.join(tmp, "manifest.json")))
+        out = {"n_q_points_1d": np.array(degree + 1 + extra)}
+        for k, v in man.items():
+            if isinstance(v, dict):
+                if k in ("q_points",) or (k == "coefficient" and op != "helmholtz_var"):
+                    continue
+                out[k] = np.fromfile(os.path.join(tmp, v["file"]), dtype=v["dtype"])
+            else:
+                out[k] = np.array(v)
+        os.makedirs(OUT_NQ, exist_ok=True)
+        np.savez_compressed(os.path.join(OUT_NQ, name + ".npz"), **out)
+        print(name, {k: v.item() for k, v in out.items() if v.ndim == 0})
+
 
 def run_gmg_case(name, spec):
     dim, degree, ref, number, coef, keep_vectors = spec[:6]
@@ -119,9 +147,11 @@ def run_case(name, spec):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    names = sys.argv[1:] or (list(CASES) + list(GMG_CASES))
+    names = sys.argv[1:] or (list(CASES) + list(GMG_CASES) + list(NQ_CASES))
     for n in names:
-        if n in GMG_CASES:
+        if n in NQ_CASES:
+            run_nq_case(n, NQ_CASES[n])
+        elif n in GMG_CASES:
             run_gmg_case(n, GMG_CASES[n])
         else:
             run_case(n, CASES[n])

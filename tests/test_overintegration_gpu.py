@@ -96,3 +96,46 @@ def test_overintegration_with_hanging_nodes_is_refused():
     with pytest.raises(dealii_b200.B200MFError):
         mf.reinit(3, 2, om.l2g.astype(np.uint32), cell_vertices=om.cell_vertices, n_owned_dofs=om.n_dofs,
                   n_q_points_1d=4, constraint_mask=mask)
+
+
+# ---- against the reference itself: ref_dump compiled with more quadrature points (tests/golden/ref_nq)
+import glob
+import os
+
+GOLDEN_NQ = os.path.join(os.path.dirname(__file__), "golden", "ref_nq")
+NQ_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_NQ, "*.npz")))
+
+
+def load_nq(name):
+    z = np.load(os.path.join(GOLDEN_NQ, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    for k in ("dim", "degree", "n_dofs", "n_cells", "n_q_points_1d"):
+        g[k] = int(g[k])
+    return g
+
+
+@pytest.mark.parametrize("name", NQ_CASES)
+@pytest.mark.parametrize("geometry", ["vertices", "jacobians"])
+def test_overintegrated_operator_matches_deal_ii(name, geometry):
+    """The arrays Portable::MatrixFree built with QGauss(fe_degree + 2) go into the engine; vmult, diagonal and
+    CG + Jacobi are compared with what Portable::MatrixFree / the CPU MatrixFree computed."""
+    g = load_nq(name)
+    dim, p, Q, nc = g["dim"], g["degree"], g["n_q_points_1d"], g["n_cells"]
+    l2g = g["local_to_global"].reshape(nc, (p + 1) ** dim).astype(np.uint32)
+    mf = dealii_b200.MatrixFree("f64")
+    kw = dict(constrained_dofs=g["constrained_dofs"].astype(np.uint32), n_owned_dofs=g["n_dofs"], n_q_points_1d=Q)
+    if geometry == "vertices":
+        mf.reinit(dim, p, l2g, cell_vertices=g["cell_vertices"].reshape(nc, 2 ** dim, dim), **kw)
+    else:
+        mf.reinit(dim, p, l2g, inv_jacobian=g["inv_jacobian"].reshape(nc, Q ** dim, dim, dim),
+                  JxW=g["JxW"].reshape(nc, Q ** dim), **kw)
+    op = str(g["op"])
+    coef = torch.from_numpy(g["coefficient"]).cuda() if op == "helmholtz_var" else None
+    A = dealii_b200.MatrixFreeOperator(mf, mass_coefficient=coef, mass_constant=0.0 if coef is not None else 10.0)
+    x = torch.from_numpy(g["src"]).cuda()
+    y = torch.zeros_like(x)
+    A.vmult(y, x)
+    per_entry(y.cpu().numpy(), g["dst_portable_matrixfree"], 1e-12)
+    diag = torch.zeros_like(x)
+    mf.compute_diagonal(A.op, diag)
+    per_entry(diag.cpu().numpy(), g["diagonal_portable"], 1e-12)
