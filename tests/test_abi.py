@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -36,7 +37,8 @@ def test_struct_layout_matches_header_sizes(tmp_path):
                "b200mf_operator": L.Operator, "b200mf_solver_desc": L.SolverDesc,
                "b200mf_solver_result": L.SolverResult, "b200mf_mesh_desc": L.MeshDesc,
                "b200mf_mesh_view": L.MeshView, "b200mf_partition_desc": L.PartitionDesc,
-               "b200mf_partition_view": L.PartitionView}
+               "b200mf_partition_view": L.PartitionView, "b200mf_mg_desc": L.MgDesc,
+               "b200mf_mg_level_info": L.MgLevelInfo, "b200mf_bulk_info": L.BulkInfo}
     src = tmp_path / "sizes.c"
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text('#include <stdio.h>\n#include "b200mf.h"\nint main(void){' + body + 'return 0;}\n')
@@ -92,3 +94,18 @@ def test_cxx_multigrid_over_the_c_abi(tmp_path):
     r = _build_cxx_example(tmp_path, "step37_like")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "35937 DoFs: CG + multigrid converged in" in r.stdout and "level 4" in r.stdout
+
+
+def test_quadrature_point_count_is_validated_before_anything_else():
+    """AssertThrow(n_q_points_1d >= fe_degree + 1) of portable_matrix_free.templates.h:1243: fewer points are an
+    invalid argument (also without a device), more are accepted up to 12."""
+    lib = L.load()
+    l2g = np.zeros(27, dtype=np.uint32)
+    for nq, expect_invalid in ((2, True), (13, True)):
+        d = L.SetupDesc()
+        d.dim, d.degree, d.n_q_points_1d, d.number = 3, 2, nq, L.F64
+        d.n_cells, d.n_owned_dofs = 1, 27
+        d.local_to_global = l2g.ctypes.data_as(C.c_void_p)
+        h = C.c_void_p()
+        rc = lib.b200mf_setup_create(C.byref(d), C.byref(h))
+        assert rc == L.ERR_INVALID and b"n_q_points_1d" in lib.b200mf_last_error()
