@@ -607,15 +607,10 @@ int b200mf_setup_create(const b200mf_setup_desc *d, b200mf_setup **out) {
                  "n_q_points_1d must be in [degree+1, 12] (got %d for degree %d)", d->n_q_points_1d,
                  d->degree);
   const bool overint = d->n_q_points_1d != d->degree + 1;
-  if (overint) {
-    bool any = false;
-    if (d->constraint_mask)
-      for (uint64_t c = 0; c < d->n_cells && !any; ++c) any = d->constraint_mask[c] != 0;
-    if (any || d->shape_values || d->shape_gradients_collocation || d->quadrature_weights) {
-      set_error("n_q_points_1d > degree+1 is supported on meshes without hanging nodes and with the engine's own "
-                "shape data");
-      return B200MF_ERR_UNSUPPORTED;
-    }
+  if (overint && (d->shape_values || d->shape_gradients_collocation || d->quadrature_weights)) {
+    set_error("n_q_points_1d > degree+1 uses the engine's own shape data (caller-provided arrays are for degree+1 "
+              "points)");
+    return B200MF_ERR_UNSUPPORTED;
   }
   B200MF_REQUIRE(d->number == B200MF_F64 || d->number == B200MF_F32, "bad number type");
   B200MF_REQUIRE(d->local_to_global || d->n_cells == 0, "local_to_global is null");

@@ -5,9 +5,13 @@
 // Q quadrature points, differentiate there (collocation derivative of the Lagrange basis in the Q Gauss
 // points), apply the quadrature-point operator, and come back with the transposed matrices.
 //
+// Hanging-node constraints are resolved on the cell's dof values before and (transposed) after, with the
+// routine of the collocation kernels.
+//
 // This is the correctness path of the engine for that case, not a tuned kernel: one CTA per cell, sizes are
 // run-time values, all tensors live in shared memory.  The fast paths (bricks, plane kernel) cover
 // n_q_points_1d == fe_degree + 1, which is what the reference's tutorials and benchmarks use.
+#include "cell_kernels.cuh"
 #include "vector_ops.cuh"
 
 namespace b200mf {
@@ -17,6 +21,8 @@ constexpr int kOverThreads = 128;
 template <typename Number>
 struct OverintParams {
   const uint32_t *l2g;
+  const uint16_t *mask;    // ConstraintKinds per cell or null
+  const Number *weights;   // subface interpolation matrix [n][n]
   const uint32_t *geom_id;
   const Number *geom_table, *metric, *jxw;
   const Number *tables; // S[n][Q] (dof basis at the quadrature points) | Dq[Q][Q] (l_a'(x_b)) | w[Q]
@@ -138,6 +144,24 @@ __device__ void apply_cell(const OverintParams<Number> &p, unsigned long long ce
   *result = const_cast<Number *>(in);
 }
 
+// resolve_hanging_nodes on the cell's n^dim values (the routine of cell_kernels.cuh needs n at compile time)
+template <int dim, typename Number, bool transpose>
+__device__ void resolve_runtime(int n, const Number *W, unsigned mask, Number *U) {
+  const int lines = dim == 2 ? n : n * n;
+  const int line = threadIdx.x;
+  const bool active = line < lines;
+  switch (n) {
+    case 2: resolve_hanging_nodes_cell<dim, 2, Number, transpose>(W, mask, U, line, active); break;
+    case 3: resolve_hanging_nodes_cell<dim, 3, Number, transpose>(W, mask, U, line, active); break;
+    case 4: resolve_hanging_nodes_cell<dim, 4, Number, transpose>(W, mask, U, line, active); break;
+    case 5: resolve_hanging_nodes_cell<dim, 5, Number, transpose>(W, mask, U, line, active); break;
+    case 6: resolve_hanging_nodes_cell<dim, 6, Number, transpose>(W, mask, U, line, active); break;
+    case 7: resolve_hanging_nodes_cell<dim, 7, Number, transpose>(W, mask, U, line, active); break;
+    case 8: resolve_hanging_nodes_cell<dim, 8, Number, transpose>(W, mask, U, line, active); break;
+    default: resolve_hanging_nodes_cell<dim, 9, Number, transpose>(W, mask, U, line, active); break;
+  }
+}
+
 template <int dim, typename Number>
 __global__ void __launch_bounds__(kOverThreads) overint_kernel(const OverintParams<Number> p) {
   extern __shared__ __align__(16) unsigned char over_smem[];
@@ -149,20 +173,25 @@ __global__ void __launch_bounds__(kOverThreads) overint_kernel(const OverintPara
   __syncthreads();
   for (unsigned long long cell = p.cell_begin + blockIdx.x; cell < p.cell_end; cell += gridDim.x) {
     const uint32_t *l2g = p.l2g + cell * npc;
+    const unsigned mask = p.mask ? p.mask[cell] : 0u; // uniform over the CTA
     Number *res = nullptr;
     if (!p.diagonal) {
       for (int i = threadIdx.x; i < npc; i += blockDim.x) {
         const uint32_t idx = l2g[i];
-        u0[i] = (idx & B200MF_L2G_CONSTRAINED) ? Number(0) : p.src[idx];
+        const Number v = (idx & B200MF_L2G_CONSTRAINED) ? Number(0) : p.src[idx];
+        u0[i] = v;
+        acc[i] = v; // the values as read, for src . (A src)
       }
       __syncthreads();
+      if (mask) resolve_runtime<dim, Number, false>(n, p.weights, mask, u0);
       apply_cell<dim, Number>(p, cell, u0, A, B, G, S, Dq, w, &res);
+      if (mask) resolve_runtime<dim, Number, true>(n, p.weights, mask, res);
       double dot = 0.0;
       for (int i = threadIdx.x; i < npc; i += blockDim.x) {
         const uint32_t idx = l2g[i];
         if (!(idx & B200MF_L2G_CONSTRAINED)) {
           atomicAdd(p.dst + idx, res[i]);
-          dot += double(u0[i]) * double(res[i]);
+          dot += double(acc[i]) * double(res[i]);
         }
       }
       if (p.dot_accum != nullptr) {
@@ -175,7 +204,9 @@ __global__ void __launch_bounds__(kOverThreads) overint_kernel(const OverintPara
       for (int j = 0; j < npc; ++j) {
         for (int i = threadIdx.x; i < npc; i += blockDim.x) u0[i] = i == j ? Number(1) : Number(0);
         __syncthreads();
+        if (mask) resolve_runtime<dim, Number, false>(n, p.weights, mask, u0);
         apply_cell<dim, Number>(p, cell, u0, A, B, G, S, Dq, w, &res);
+        if (mask) resolve_runtime<dim, Number, true>(n, p.weights, mask, res);
         if (threadIdx.x == 0) acc[j] = res[j];
         __syncthreads();
       }
@@ -193,6 +224,7 @@ static int launch_overint_t(const Setup &s, const b200mf_operator &op, void *dst
                             uint64_t ce, cudaStream_t st, double *dot, bool diagonal) {
   OverintParams<Number> p;
   p.l2g = s.d_l2g; p.geom_id = s.d_geom_id;
+  p.mask = s.any_mask ? s.d_mask : nullptr; p.weights = (const Number *)s.d_weights;
   p.geom_table = (const Number *)s.d_geom_table; p.metric = (const Number *)s.d_metric; p.jxw = (const Number *)s.d_jxw;
   p.tables = (const Number *)s.d_overint_tables;
   p.src = (const Number *)src; p.dst = (Number *)dst;

@@ -78,8 +78,8 @@ typedef struct {
   int dim;           /* 2 or 3                                                          */
   int degree;        /* FE_Q degree p, 1..8                                             */
   int n_q_points_1d; /* QGauss points per direction, in [p+1, 12].  p+1 runs the tuned (collocation)
-                        kernels; more points (over-integration) run a plain per-cell kernel and need a
-                        mesh without hanging nodes                                                    */
+                        kernels; more points (over-integration) run a plain per-cell kernel (all cell
+                        kinds, hanging nodes included)                                                */
   int number;        /* B200MF_F64 / B200MF_F32: arithmetic AND vector element type     */
   uint64_t n_cells;  /* locally owned cells                                             */
   uint64_t n_owned_dofs; /* Partitioner::locally_owned_size()                           */

@@ -77,6 +77,8 @@ NQ_CASES = {
     "nq_q2_e1_deformed_var": (3, 2, 1, 2, "deformed", "helmholtz_var", 1),
     "nq_q3_e1_cartesian": (3, 3, 1, 1, "cartesian", "helmholtz", 0),
     "nq_d2_q2_e1_cartesian_var": (2, 2, 1, 3, "cartesian", "helmholtz_var", 1),
+    "nq_q2_e1_hanging_var": (3, 2, 1, 2, "hanging", "helmholtz_var", 1),
+    "nq_d2_q3_e1_hanging": (2, 3, 1, 3, "hanging", "helmholtz", 0),
 }
 OUT_NQ = os.path.join(ROOT, "tests", "golden", "ref_nq")
 

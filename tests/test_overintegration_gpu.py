@@ -88,16 +88,6 @@ def test_overintegrated_operator_matches_the_oracle(dim, degree, extra, refineme
         assert np.abs(xs.cpu().numpy() - ref["x"]).max() < 1e-8 * np.abs(ref["x"]).max()
 
 
-def test_overintegration_with_hanging_nodes_is_refused():
-    om = OracleMesh(3, 2, refinements=1)
-    mask = np.zeros(om.n_cells, dtype=np.uint16)
-    mask[0] = 9
-    mf = dealii_b200.MatrixFree("f64")
-    with pytest.raises(dealii_b200.B200MFError):
-        mf.reinit(3, 2, om.l2g.astype(np.uint32), cell_vertices=om.cell_vertices, n_owned_dofs=om.n_dofs,
-                  n_q_points_1d=4, constraint_mask=mask)
-
-
 # ---- against the reference itself: ref_dump compiled with more quadrature points (tests/golden/ref_nq)
 import glob
 import os
@@ -124,6 +114,9 @@ def test_overintegrated_operator_matches_deal_ii(name, geometry):
     l2g = g["local_to_global"].reshape(nc, (p + 1) ** dim).astype(np.uint32)
     mf = dealii_b200.MatrixFree("f64")
     kw = dict(constrained_dofs=g["constrained_dofs"].astype(np.uint32), n_owned_dofs=g["n_dofs"], n_q_points_1d=Q)
+    if g["constraint_mask"].any():
+        # hanging nodes: ConstraintKinds masks and redirected index lists as Portable::MatrixFree built them
+        kw["constraint_mask"] = g["constraint_mask"].astype(np.uint16)
     if geometry == "vertices":
         mf.reinit(dim, p, l2g, cell_vertices=g["cell_vertices"].reshape(nc, 2 ** dim, dim), **kw)
     else:
@@ -139,3 +132,11 @@ def test_overintegrated_operator_matches_deal_ii(name, geometry):
     diag = torch.zeros_like(x)
     mf.compute_diagonal(A.op, diag)
     per_entry(diag.cpu().numpy(), g["diagonal_portable"], 1e-12)
+    if "cg_jacobi_iterations" in g:
+        b = torch.ones_like(x)
+        mf.set_constrained_values(0.0, b)
+        inv = A.compute_diagonal()
+        xs = mf.initialize_dof_vector()
+        control = dealii_b200.SolverControl(2000, float(g["cg_tolerance"]))
+        dealii_b200.SolverCG(control).solve(A, xs, b, inv)
+        assert abs(control.last_step() - int(g["cg_jacobi_iterations"])) <= 1
